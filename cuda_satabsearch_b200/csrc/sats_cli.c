@@ -1,0 +1,243 @@
+/*
+ * sats_cli.c -- drop-in `cudaSaTabsearch` command line over the libsats C ABI (include/sats.h).
+ *
+ * Keeps the reference driver's contract (stivalaa/cuda_satabsearch nvcc_src_current/cudaSaTabsearch.cu):
+ *   argv   -c | -q dbfile | -r restarts                    (:605-626)
+ *   stdin  db path / "LTYPE LORDER LSOLN" / query structures   (:667-693), or with -q a list of ids (:631-664)
+ *   stdout per (pool, query): three '#' lines then "name rawscore norm2score z-score p-value"
+ *          rows (+ SSE map pairs when LSOLN=T), all queries on the small pool (order <= 96) first,
+ *          then all queries on the large pool (:987-1115, :1196-1269, :1272-1310)
+ *   stderr diagnostics and timings; errors are "message + exit status 1"
+ * Row formatting follows the `-c` path (:442-454), which is what the north star pins parity to.
+ *
+ * Differences, all deliberate: -c is refused (this build has no CPU search path); -q computes norm2 with the
+ * query's own order like the reference's CPU branch (:366, :380) rather than the GPU branch's orders[qi]
+ * (:996-998); the db file may also be a packed SATSDB1 cache.  Extra options:
+ *   -g N      use N GPUs (cost-weighted shards of the size-sorted db; Philox mode only)
+ *   -R mode   philox (default) | xorwow  -- xorwow = the reference GPU run's 128x128 cuRAND streams
+ *   -A mode   table (default) | fast     -- Metropolis thresholds: host libm table | device fast-math
+ *   -s seed   RNG seed (default 1234)
+ */
+#include <getopt.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "sats.h"
+
+#define MAX_GPUS 16
+
+static double now_ms(void)
+{
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return t.tv_sec * 1e3 + t.tv_nsec * 1e-6;
+}
+
+static void die(const char *what)
+{
+  fprintf(stderr, "%s: %s\n", what, sats_last_error());
+  exit(1);
+}
+
+static void usage(const char *prog)
+{
+  fprintf(stderr, "Usage: %s [-c] [-q dbfile] [-r restarts] [-g gpus] [-R philox|xorwow] [-A table|fast] [-s seed]\n", prog);
+  fprintf(stderr, "  -c : (reference: run on host CPU) not available in this build\n");
+  fprintf(stderr, "  -q dbfile : database is read from dbfile, list of query\n"
+                  "              ids is read from stdin\n");
+  fprintf(stderr, "   -r restarts : number of restarts. Default %d\n", SATS_DEFAULT_MAXSTART);
+  exit(1);
+}
+
+static char *read_all(FILE *fp, size_t *len)
+{
+  size_t cap = 1 << 16, n = 0;
+  char *buf = (char *)malloc(cap);
+  if (!buf) return NULL;
+  for (;;) {
+    size_t got = fread(buf + n, 1, cap - n, fp);
+    n += got;
+    if (got == 0) break;
+    if (n == cap) {
+      cap *= 2;
+      char *nb = (char *)realloc(buf, cap);
+      if (!nb) { free(buf); return NULL; }
+      buf = nb;
+    }
+  }
+  *len = n;
+  return buf;
+}
+
+static int load_db(const char *path, sats_db **db)
+{
+  FILE *fp = fopen(path, "rb");
+  char magic[8] = {0};
+  if (!fp) { fprintf(stderr, "ERROR opening db file %s\n", path); exit(1); }
+  size_t got = fread(magic, 1, 8, fp);
+  fclose(fp);
+  if (got == 8 && memcmp(magic, "SATSDB1", 8) == 0) return sats_db_read_packed(path, db);
+  return sats_db_read_ascii(path, db);
+}
+
+int main(int argc, char *argv[])
+{
+  char dbfile[4096] = "";
+  int querydbmode = 0, maxstart = SATS_DEFAULT_MAXSTART, ngpus = 1, c;
+  int rng_mode = SATS_RNG_PHILOX, accept_mode = SATS_ACCEPT_HOST_TABLE;
+  unsigned long long seed = SATS_REF_SEED;
+  int flags[3] = {1, 1, 0};
+  sats_db *db = NULL, *queries = NULL;
+
+  while ((c = getopt(argc, argv, "cq:r:g:R:A:s:")) != -1) {
+    switch (c) {
+      case 'c':
+        fprintf(stderr, "ERROR: -c (host CPU search) is not available: this build is GPU-only\n");
+        exit(1);
+      case 'q': querydbmode = 1; strncpy(dbfile, optarg, sizeof(dbfile) - 1); break;
+      case 'r': maxstart = atoi(optarg); break;
+      case 'g': ngpus = atoi(optarg); break;
+      case 'R':
+        if (!strcmp(optarg, "philox")) rng_mode = SATS_RNG_PHILOX;
+        else if (!strcmp(optarg, "xorwow")) rng_mode = SATS_RNG_XORWOW_GRID;
+        else usage(argv[0]);
+        break;
+      case 'A':
+        if (!strcmp(optarg, "table")) accept_mode = SATS_ACCEPT_HOST_TABLE;
+        else if (!strcmp(optarg, "fast")) accept_mode = SATS_ACCEPT_DEVICE_FAST;
+        else usage(argv[0]);
+        break;
+      case 's': seed = strtoull(optarg, NULL, 0); break;
+      default: usage(argv[0]);
+    }
+  }
+  if (maxstart < 1) { fprintf(stderr, "ERROR: restarts must be >= 1\n"); exit(1); }
+  if (ngpus < 1 || ngpus > MAX_GPUS) { fprintf(stderr, "ERROR: -g must be 1..%d\n", MAX_GPUS); exit(1); }
+  if (ngpus > 1 && rng_mode == SATS_RNG_XORWOW_GRID) {
+    fprintf(stderr, "ERROR: -R xorwow reproduces a single-GPU reference run; use -g 1\n");
+    exit(1);
+  }
+  fprintf(stderr, "MAXDIM = %d\n", SATS_MAXDIM);
+
+  size_t inlen = 0;
+  char *input = read_all(stdin, &inlen);
+  if (!input) { fprintf(stderr, "ERROR reading stdin\n"); exit(1); }
+
+  char *ids = NULL;
+  int num_queries = 0;
+  if (querydbmode) {
+    flags[0] = 1; flags[1] = 1; flags[2] = 0;
+    int cap = 1;
+    for (size_t i = 0; i < inlen; i++) cap += input[i] == '\n';
+    ids = (char *)calloc((size_t)cap + 1, 9);
+    num_queries = sats_idlist_parse(input, inlen, ids, cap + 1);
+    if (num_queries < 0) die("ERROR reading query ids");
+  } else {
+    if (sats_input_parse(input, inlen, dbfile, sizeof dbfile, flags, &queries) != SATS_OK) {
+      fprintf(stderr, "%s\n", sats_last_error());
+      fprintf(stderr, "ERROR loading query structures from stdin\n");
+      exit(1);
+    }
+    num_queries = sats_db_count(queries);
+    fprintf(stderr, "Read %d query structures\n", num_queries);
+  }
+  if (!flags[0]) {
+    fprintf(stderr, "WARNING: LTYPE is always set to T\n");
+    flags[0] = 1;
+  }
+  const int lorder = flags[1], lsoln = flags[2];
+
+  fprintf(stderr, "Loading database...\n");
+  double t0 = now_ms();
+  if (load_db(dbfile, &db) != SATS_OK) { fprintf(stderr, "%s\n", sats_last_error()); fprintf(stderr, "ERROR loading database\n"); exit(1); }
+  const int dbsize = sats_db_count(db);
+  int *small_idx = (int *)malloc(sizeof(int) * (size_t)(dbsize + 1));
+  int *large_idx = (int *)malloc(sizeof(int) * (size_t)(dbsize + 1));
+  int nsmall = 0, nlarge = 0;
+  for (int i = 0; i < dbsize; i++) {
+    if (sats_db_order(db, i) <= SATS_MAXDIM_GPU) small_idx[nsmall++] = i;
+    else large_idx[nlarge++] = i;
+  }
+  fprintf(stderr, "Loaded %d db entries (%d order > %d) in %f ms\n", dbsize, nlarge, SATS_MAXDIM_GPU, now_ms() - t0);
+
+  if (querydbmode) {
+    fprintf(stderr, "Building query index list...\n");
+    int *qidx = (int *)malloc(sizeof(int) * (size_t)(num_queries + 1));
+    for (int i = 0; i < num_queries; i++) {
+      qidx[i] = sats_db_find(db, ids + (size_t)i * 9);
+      if (qidx[i] < 0) { fprintf(stderr, "%s\n", sats_last_error()); exit(1); }
+    }
+    if (sats_db_select(db, qidx, num_queries, &queries) != SATS_OK) die("ERROR building query set");
+    free(qidx);
+  }
+  if (num_queries == 0) { fprintf(stderr, "ERROR: no query structures found on stdin\n"); exit(1); }
+
+  int have = sats_device_count();
+  if (have < 1) { fprintf(stderr, "ERROR: no CUDA device found (this build has no CPU search path)\n"); exit(1); }
+  if (ngpus > have) { fprintf(stderr, "ERROR: %d GPUs requested, %d present\n", ngpus, have); exit(1); }
+  fprintf(stderr, "maxstart = %d\n", maxstart);
+  fprintf(stderr, "Copying database to device...\n");
+  t0 = now_ms();
+  sats_searcher *sr[MAX_GPUS];
+  for (int g = 0; g < ngpus; g++)
+    if (sats_searcher_create(db, g, g, ngpus, &sr[g]) != SATS_OK) die("ERROR creating searcher");
+  fprintf(stderr, "Copied %d entries to %d GPU(s) in %f ms\n", dbsize, ngpus, now_ms() - t0);
+
+  sats_params prm;
+  sats_params_default(&prm);
+  prm.lorder = lorder; prm.lsoln = lsoln; prm.restarts = maxstart;
+  prm.rng_mode = rng_mode; prm.accept_mode = accept_mode; prm.seed = seed;
+  prm.pool_threshold = SATS_MAXDIM_GPU;
+
+  /* queries are processed in chunks that bound the result buffers */
+  size_t per_query = (size_t)dbsize * (lsoln ? (SATS_MAP_STRIDE + 1) : 1) * sizeof(int32_t);
+  int chunk = (int)((256u << 20) / (per_query ? per_query : 1));
+  if (chunk < 1) chunk = 1;
+  if (chunk > num_queries) chunk = num_queries;
+  int32_t *scores = (int32_t *)malloc(sizeof(int32_t) * (size_t)chunk * (size_t)(dbsize + 1));
+  int32_t *maps = lsoln ? (int32_t *)malloc(sizeof(int32_t) * (size_t)chunk * (size_t)(dbsize + 1) * SATS_MAP_STRIDE) : NULL;
+  size_t outcap = 1 << 20;
+  char *out = (char *)malloc(outcap);
+  if (!scores || (lsoln && !maps) || !out) { fprintf(stderr, "malloc scores failed\n"); exit(1); }
+
+  for (int pass = 0; pass < 2; pass++) {
+    const int *idx = pass == 0 ? small_idx : large_idx;
+    const int n = pass == 0 ? nsmall : nlarge;
+    if (pass == 1 && n == 0) break;
+    prm.pool = pass == 0 ? SATS_POOL_SMALL : SATS_POOL_LARGE;
+    for (int q0 = 0; q0 < num_queries; q0 += chunk) {
+      const int nq = (num_queries - q0) < chunk ? (num_queries - q0) : chunk;
+      double t1 = now_ms();
+      for (int g = 0; g < ngpus; g++)
+        if (sats_search_upload(sr[g], queries, q0, nq) != SATS_OK) die("ERROR uploading queries");
+      for (int g = 0; g < ngpus; g++)
+        if (sats_search_launch(sr[g], &prm, (uint32_t)q0, NULL) != SATS_OK) die("kernel launch failed");
+      for (int g = 0; g < ngpus; g++)
+        if (sats_search_collect(sr[g], scores, maps) != SATS_OK) die("ERROR collecting results");
+      double ms = now_ms() - t1;
+      fprintf(stderr, "GPU execution time %f ms (%d queries x %d entries, %s pool)\n", ms, nq, n, pass ? "large" : "small");
+      fprintf(stderr, "%f million iterations/sec\n", ((double)nq * n * ((double)maxstart * SATS_MAXITER) / (ms / 1000)) / 1.0e6);
+      for (int q = 0; q < nq; q++) {
+        const int32_t *sc = scores + (size_t)q * dbsize;
+        const int32_t *mp = lsoln ? maps + (size_t)q * dbsize * SATS_MAP_STRIDE : NULL;
+        size_t need = sats_format_block(out, outcap, sats_db_name(queries, q0 + q), sats_db_order(queries, q0 + q),
+                                        dbfile, lorder, lsoln, db, idx, n, sc, mp);
+        if (need >= outcap) {
+          outcap = need + 1;
+          out = (char *)realloc(out, outcap);
+          if (!out) { fprintf(stderr, "malloc failed\n"); exit(1); }
+          sats_format_block(out, outcap, sats_db_name(queries, q0 + q), sats_db_order(queries, q0 + q), dbfile, lorder,
+                            lsoln, db, idx, n, sc, mp);
+        }
+        fwrite(out, 1, need, stdout);
+      }
+    }
+  }
+  for (int g = 0; g < ngpus; g++) sats_searcher_free(sr[g]);
+  sats_db_free(db);
+  sats_db_free(queries);
+  free(scores); free(maps); free(out); free(small_idx); free(large_idx); free(ids); free(input);
+  return 0;
+}

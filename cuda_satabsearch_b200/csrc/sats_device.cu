@@ -1,0 +1,508 @@
+// sats_device.cu -- device half of libsats: the searcher (device-resident packed database, query upload,
+// kernel dispatch, result gather).  Replaces, for the hot path, the host driver code around the reference's
+// kernel launches: db upload cudaSaTabsearch.cu:924-967, copyQueryToConstantMemory :486-558, init_rng :258-264
+// and :896-922, the launches :1042/:1223 and the result copies :1075-1087.
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include <curand_kernel.h>
+
+#include "sats_internal.h"
+#include "sats_kernel.cuh"
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return sats_fail(SATS_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, \
+                       cudaGetErrorString(e_));                                                          \
+  } while (0)
+
+static const int kScoreSentinel = (int)0x80808080;   // byte-memset pattern marking "not computed by this launch"
+static const int kMaxSmem = 227 * 1024;
+
+// the reference's init_rng (cudaSaTabsearch.cu:258-264): curand_init(seed, tid, 0) for the 128 x 128 grid
+__global__ void sats_xorwow_init_kernel(uint32_t *states, int n, unsigned long long seed)
+{
+  int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n) return;
+  curandStateXORWOW_t st;
+  curand_init(seed, (unsigned long long)tid, 0ull, &st);
+  uint32_t *o = states + (size_t)tid * 6;
+  o[0] = st.d;
+  for (int k = 0; k < 5; k++) o[1 + k] = st.v[k];
+}
+
+struct sats_searcher {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int db_count = 0;                       // entries of the whole database (output indexing)
+  std::vector<int32_t> sorted_orig;       // local sorted position -> original db index (decreasing order)
+  std::vector<int32_t> sorted_order;
+  std::vector<int32_t> file_rank;         // local sorted position -> rank in original file order among local entries
+  uint8_t *d_blobs = nullptr;
+  uint64_t *d_blob_off = nullptr;
+  uint32_t *d_blob_bytes = nullptr;
+  float *d_accept = nullptr;
+  uint32_t *d_xw = nullptr;
+  bool xw_ready = false;
+  uint64_t xw_seed = 0;
+  int32_t *d_pool_list = nullptr;
+  int32_t *d_xw_blocks = nullptr;
+  // queries
+  uint8_t *d_qblobs = nullptr; size_t qblob_cap = 0;
+  uint64_t *d_qoff = nullptr; uint32_t *d_qbytes = nullptr; int qmeta_cap = 0;
+  uint8_t *h_qstage = nullptr; size_t h_qstage_cap = 0;
+  std::vector<int> q_n1;
+  std::vector<uint32_t> q_bytes;
+  // results
+  int32_t *d_scores = nullptr; int8_t *d_maps = nullptr;
+  int32_t *h_scores = nullptr; int8_t *h_maps = nullptr;
+  size_t score_cap = 0, map_cap = 0;
+  int last_q = 0, last_lsoln = 0;
+  long long launches = 0;
+  bool attr_done = false;
+};
+
+typedef void (*kernel_fn)(const SatsKParams);
+template <int W1, int W2> static kernel_fn pick2(bool lorder, bool xorwow)
+{
+  if (xorwow) return lorder ? sats_anneal_kernel<W1, W2, true, true> : sats_anneal_kernel<W1, W2, false, true>;
+  return lorder ? sats_anneal_kernel<W1, W2, true, false> : sats_anneal_kernel<W1, W2, false, false>;
+}
+static kernel_fn pick_kernel(int w1, int w2, bool lorder, bool xorwow)
+{
+  switch (w1 * 8 + w2) {
+    case 1 * 8 + 1: return pick2<1, 1>(lorder, xorwow);
+    case 1 * 8 + 2: return pick2<1, 2>(lorder, xorwow);
+    case 1 * 8 + 4: return pick2<1, 4>(lorder, xorwow);
+    case 2 * 8 + 1: return pick2<2, 1>(lorder, xorwow);
+    case 2 * 8 + 2: return pick2<2, 2>(lorder, xorwow);
+    case 2 * 8 + 4: return pick2<2, 4>(lorder, xorwow);
+    case 4 * 8 + 1: return pick2<4, 1>(lorder, xorwow);
+    case 4 * 8 + 2: return pick2<4, 2>(lorder, xorwow);
+    default: return pick2<4, 4>(lorder, xorwow);
+  }
+}
+static int words_for(int n) { return n <= 32 ? 1 : (n <= 64 ? 2 : 4); }
+static size_t round16(size_t x) { return (x + 15) & ~(size_t)15; }
+static size_t entry_blob_bytes(int n) { return round16(SATS_K_ENTRY_HDR + 8 * (size_t)n * n); }
+static size_t query_blob_bytes(int n) { return round16(SATS_K_QUERY_HDR + 8 * (size_t)n * n); }
+
+static void fill_cells(const sats_db *db, int e, uint8_t *cells)
+{
+  int n = db->order[e];
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) {
+      float d = db->dist(e, i, j);
+      uint32_t code = db->code(e, i, j);
+      memcpy(cells + 8 * ((size_t)i * n + j), &d, 4);
+      memcpy(cells + 8 * ((size_t)i * n + j) + 4, &code, 4);
+    }
+}
+
+extern "C" int sats_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" int sats_searcher_create(const sats_db *db, int device, int shard_rank, int shard_count, sats_searcher **out)
+{
+  if (!db || !out) return sats_fail(SATS_ERR_ARG, "sats_searcher_create: null argument");
+  if (shard_count < 1) shard_count = 1;
+  if (shard_rank < 0 || shard_rank >= shard_count) return sats_fail(SATS_ERR_ARG, "bad shard %d of %d", shard_rank, shard_count);
+  int ndev = sats_device_count();
+  if (ndev < 1) return sats_fail(SATS_ERR_CUDA, "no CUDA device available (this library has no CPU search path)");
+  if (device < 0 || device >= ndev) return sats_fail(SATS_ERR_ARG, "device %d out of range (have %d)", device, ndev);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return sats_fail(SATS_ERR_CUDA, "device %d is sm_%d%d; this build targets sm_100a", device, prop.major, prop.minor);
+
+  sats_searcher *s = new sats_searcher();
+  s->device = device;
+  s->db_count = db->count();
+  std::vector<int32_t> owner((size_t)db->count(), 0);
+  if (shard_count > 1) sats_partition(db, shard_count, owner.data());
+  std::vector<int32_t> local;
+  for (int e = 0; e < db->count(); e++) if (owner[e] == shard_rank) local.push_back(e);
+  std::vector<int32_t> pos(local.size());
+  std::iota(pos.begin(), pos.end(), 0);
+  std::stable_sort(pos.begin(), pos.end(), [&](int a, int b) { return db->order[local[a]] > db->order[local[b]]; });
+  size_t total = 0;
+  std::vector<uint64_t> off(local.size());
+  std::vector<uint32_t> bytes(local.size());
+  for (size_t k = 0; k < local.size(); k++) {
+    int e = local[pos[k]];
+    s->sorted_orig.push_back(e);
+    s->sorted_order.push_back(db->order[e]);
+    s->file_rank.push_back(pos[k]);
+    off[k] = total;
+    bytes[k] = (uint32_t)entry_blob_bytes(db->order[e]);
+    total += bytes[k];
+  }
+  std::vector<uint8_t> blobs(total ? total : 16, 0);
+  for (size_t k = 0; k < local.size(); k++) {
+    int e = s->sorted_orig[k], n = db->order[e];
+    uint8_t *b = blobs.data() + off[k];
+    int32_t hdr[4] = {n, e, 0, 0};
+    memcpy(b, hdr, 16);
+    uint32_t tm[4][4] = {{0}};
+    for (int j = 0; j < n; j++) tm[db->code(e, j, j) & 3][j >> 5] |= 1u << (j & 31);
+    memcpy(b + 16, tm, 64);
+    fill_cells(db, e, b + SATS_K_ENTRY_HDR);
+  }
+  auto fail = [&](int rc) { sats_searcher_free(s); return rc; };
+#define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(sats_fail(SATS_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_))); } while (0)
+  CKF(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  CKF(cudaEventCreate(&s->ev0));
+  CKF(cudaEventCreate(&s->ev1));
+  CKF(cudaMalloc(&s->d_blobs, blobs.size()));
+  CKF(cudaMalloc(&s->d_blob_off, std::max<size_t>(1, local.size()) * 8));
+  CKF(cudaMalloc(&s->d_blob_bytes, std::max<size_t>(1, local.size()) * 4));
+  CKF(cudaMalloc(&s->d_pool_list, std::max<size_t>(1, local.size()) * 4));
+  CKF(cudaMalloc(&s->d_xw_blocks, SATS_REF_GRID_BLOCKS * 4));
+  CKF(cudaMemcpy(s->d_blobs, blobs.data(), blobs.size(), cudaMemcpyHostToDevice));
+  if (!local.empty()) {
+    CKF(cudaMemcpy(s->d_blob_off, off.data(), local.size() * 8, cudaMemcpyHostToDevice));
+    CKF(cudaMemcpy(s->d_blob_bytes, bytes.data(), local.size() * 4, cudaMemcpyHostToDevice));
+  }
+  // Metropolis thresholds and temperatures exactly as the reference's host path evaluates them
+  std::vector<float> temps(SATS_K_MOVES), tab((size_t)SATS_K_MOVES * (SATS_K_DCLAMP + 1));
+  float t = 10.0f;
+  for (int m = 0; m < SATS_K_MOVES; m++) {
+    temps[m] = t;
+    for (int d = 0; d <= SATS_K_DCLAMP; d++) tab[(size_t)m * (SATS_K_DCLAMP + 1) + d] = expf((float)(-d) / t);
+    t *= 0.95f;
+  }
+  CKF(cudaMalloc(&s->d_accept, tab.size() * 4));
+  CKF(cudaMemcpy(s->d_accept, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+  CKF(cudaMemcpyToSymbol(c_sats_temps, temps.data(), temps.size() * 4));
+  CKF(cudaMalloc(&s->d_xw, (size_t)SATS_REF_GRID_BLOCKS * SATS_REF_GRID_THREADS * 6 * 4));
+#undef CKF
+  *out = s;
+  return SATS_OK;
+}
+
+extern "C" void sats_searcher_free(sats_searcher *s)
+{
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  cudaFree(s->d_blobs); cudaFree(s->d_blob_off); cudaFree(s->d_blob_bytes); cudaFree(s->d_accept); cudaFree(s->d_xw);
+  cudaFree(s->d_pool_list); cudaFree(s->d_xw_blocks); cudaFree(s->d_qblobs); cudaFree(s->d_qoff); cudaFree(s->d_qbytes);
+  cudaFree(s->d_scores); cudaFree(s->d_maps);
+  cudaFreeHost(s->h_qstage); cudaFreeHost(s->h_scores); cudaFreeHost(s->h_maps);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+extern "C" int sats_searcher_entry_count(const sats_searcher *s) { return s ? (int)s->sorted_orig.size() : 0; }
+extern "C" int sats_searcher_device(const sats_searcher *s) { return s ? s->device : -1; }
+extern "C" long long sats_searcher_launch_count(const sats_searcher *s) { return s ? s->launches : 0; }
+
+extern "C" int sats_searcher_sync(sats_searcher *s)
+{
+  if (!s) return sats_fail(SATS_ERR_ARG, "null searcher");
+  CK(cudaSetDevice(s->device));
+  CK(cudaStreamSynchronize(s->stream));
+  return SATS_OK;
+}
+
+extern "C" int sats_searcher_reset_xorwow(sats_searcher *s, uint64_t seed)
+{
+  if (!s) return sats_fail(SATS_ERR_ARG, "null searcher");
+  CK(cudaSetDevice(s->device));
+  const int n = SATS_REF_GRID_BLOCKS * SATS_REF_GRID_THREADS;
+  sats_xorwow_init_kernel<<<SATS_REF_GRID_BLOCKS, SATS_REF_GRID_THREADS, 0, s->stream>>>(s->d_xw, n, seed);
+  CK(cudaGetLastError());
+  s->launches++;
+  s->xw_ready = true;
+  s->xw_seed = seed;
+  return SATS_OK;
+}
+
+extern "C" int sats_searcher_get_xorwow(sats_searcher *s, uint32_t *states6)
+{
+  if (!s || !states6) return sats_fail(SATS_ERR_ARG, "null argument");
+  CK(cudaSetDevice(s->device));
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaMemcpy(states6, s->d_xw, (size_t)SATS_REF_GRID_BLOCKS * SATS_REF_GRID_THREADS * 24, cudaMemcpyDeviceToHost));
+  return SATS_OK;
+}
+
+extern "C" int sats_search_upload(sats_searcher *s, const sats_db *queries, int qfirst, int qcount)
+{
+  if (!s || !queries || qcount < 1 || qfirst < 0 || qfirst + qcount > queries->count())
+    return sats_fail(SATS_ERR_ARG, "sats_search_upload: bad query range");
+  CK(cudaSetDevice(s->device));
+  CK(cudaStreamSynchronize(s->stream));   // staging buffers may still be in flight
+  size_t total = 0;
+  std::vector<uint64_t> off((size_t)qcount);
+  s->q_n1.assign((size_t)qcount, 0);
+  s->q_bytes.assign((size_t)qcount, 0);
+  for (int q = 0; q < qcount; q++) {
+    int n = queries->order[qfirst + q];
+    s->q_n1[q] = n;
+    off[q] = total;
+    s->q_bytes[q] = (uint32_t)query_blob_bytes(n);
+    total += s->q_bytes[q];
+  }
+  size_t meta = (size_t)qcount * 12;
+  if (total + meta > s->h_qstage_cap) {
+    cudaFreeHost(s->h_qstage);
+    s->h_qstage = nullptr;
+    s->h_qstage_cap = 0;
+    CK(cudaMallocHost(&s->h_qstage, total + meta));
+    s->h_qstage_cap = total + meta;
+  }
+  if (total > s->qblob_cap) {
+    cudaFree(s->d_qblobs);
+    s->d_qblobs = nullptr;
+    s->qblob_cap = 0;
+    CK(cudaMalloc(&s->d_qblobs, total));
+    s->qblob_cap = total;
+  }
+  if (qcount > s->qmeta_cap) {
+    cudaFree(s->d_qoff); cudaFree(s->d_qbytes);
+    s->d_qoff = nullptr; s->d_qbytes = nullptr; s->qmeta_cap = 0;
+    CK(cudaMalloc(&s->d_qoff, (size_t)qcount * 8));
+    CK(cudaMalloc(&s->d_qbytes, (size_t)qcount * 4));
+    s->qmeta_cap = qcount;
+  }
+  memset(s->h_qstage, 0, total);
+  for (int q = 0; q < qcount; q++) {
+    int e = qfirst + q, n = queries->order[e];
+    uint8_t *b = s->h_qstage + off[q];
+    int32_t hdr[4] = {n, 0, 0, 0};     // hdr[1] (Philox query index) is patched at launch via q_index_base
+    memcpy(b, hdr, 16);
+    for (int i = 0; i < n; i++) b[16 + i] = queries->code(e, i, i);
+    fill_cells(queries, e, b + SATS_K_QUERY_HDR);
+  }
+  memcpy(s->h_qstage + total, off.data(), (size_t)qcount * 8);
+  memcpy(s->h_qstage + total + (size_t)qcount * 8, s->q_bytes.data(), (size_t)qcount * 4);
+  CK(cudaMemcpyAsync(s->d_qblobs, s->h_qstage, total, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaMemcpyAsync(s->d_qoff, s->h_qstage + total, (size_t)qcount * 8, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaMemcpyAsync(s->d_qbytes, s->h_qstage + total + (size_t)qcount * 8, (size_t)qcount * 4, cudaMemcpyHostToDevice, s->stream));
+  s->last_q = qcount;
+  return SATS_OK;
+}
+
+// writes the Philox query index into the device copies of the query headers
+__global__ void sats_patch_query_index(uint8_t *qblobs, const uint64_t *qoff, int qcount, uint32_t base)
+{
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < qcount) reinterpret_cast<uint32_t *>(qblobs + qoff[q])[1] = base + (uint32_t)q;
+}
+
+static int ensure_results(sats_searcher *s, int qcount, int lsoln)
+{
+  size_t n = (size_t)qcount * std::max<size_t>(1, s->sorted_orig.size());
+  if (n > s->score_cap) {
+    cudaFree(s->d_scores); cudaFreeHost(s->h_scores);
+    s->d_scores = nullptr; s->h_scores = nullptr; s->score_cap = 0;
+    CK(cudaMalloc(&s->d_scores, n * 4));
+    CK(cudaMallocHost(&s->h_scores, n * 4));
+    s->score_cap = n;
+  }
+  if (lsoln && n > s->map_cap) {
+    cudaFree(s->d_maps); cudaFreeHost(s->h_maps);
+    s->d_maps = nullptr; s->h_maps = nullptr; s->map_cap = 0;
+    CK(cudaMalloc(&s->d_maps, n * SATS_K_MAPROW));
+    CK(cudaMallocHost(&s->h_maps, n * SATS_K_MAPROW));
+    s->map_cap = n;
+  }
+  return SATS_OK;
+}
+
+static int set_attrs_once(sats_searcher *s)
+{
+  if (s->attr_done) return SATS_OK;
+  const int ws[3] = {1, 2, 4};
+  for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++)
+      for (int lo = 0; lo < 2; lo++)
+        for (int xw = 0; xw < 2; xw++)
+          CK(cudaFuncSetAttribute(pick_kernel(ws[a], ws[b], lo, xw), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  s->attr_done = true;
+  return SATS_OK;
+}
+
+// upper bounds (entry order) of the launch buckets: each bucket is one launch with its own shared-memory sizing
+static const int kBucketBounds[] = {8, 12, 16, 20, 24, 32, 48, 64, 96, SATS_MAXDIM};
+
+extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint32_t query_index_base, float *elapsed_ms)
+{
+  if (!s || !pp) return sats_fail(SATS_ERR_ARG, "sats_search_launch: null argument");
+  if (s->last_q < 1) return sats_fail(SATS_ERR_ARG, "sats_search_launch: no queries uploaded");
+  if (pp->restarts < 1) return sats_fail(SATS_ERR_ARG, "restarts must be >= 1");
+  CK(cudaSetDevice(s->device));
+  int rc = set_attrs_once(s);
+  if (rc) return rc;
+  const int D = (int)s->sorted_orig.size();
+  const int Q = s->last_q;
+  const bool xorwow = pp->rng_mode == SATS_RNG_XORWOW_GRID;
+  const int thr = pp->pool_threshold > 0 ? pp->pool_threshold : SATS_MAXDIM_GPU;
+  const uint64_t seed = pp->seed ? pp->seed : SATS_REF_SEED;
+  rc = ensure_results(s, Q, pp->lsoln);
+  if (rc) return rc;
+  s->last_lsoln = pp->lsoln;
+  CK(cudaMemsetAsync(s->d_scores, 0x80, (size_t)Q * std::max(1, D) * 4, s->stream));
+  if (elapsed_ms) CK(cudaEventRecord(s->ev0, s->stream));
+  sats_patch_query_index<<<(Q + 127) / 128, 128, 0, s->stream>>>(s->d_qblobs, s->d_qoff, Q, query_index_base);
+  CK(cudaGetLastError());
+  s->launches++;
+
+  // pool -> contiguous range of the (decreasing-order) sorted list
+  int first_small = 0;
+  while (first_small < D && s->sorted_order[first_small] > thr) first_small++;
+  int r0 = 0, r1 = D;
+  if (pp->pool == SATS_POOL_SMALL) r0 = first_small;
+  else if (pp->pool == SATS_POOL_LARGE) r1 = first_small;
+
+  SatsKParams k;
+  memset(&k, 0, sizeof k);
+  k.blobs = s->d_blobs; k.blob_off = s->d_blob_off; k.blob_bytes = s->d_blob_bytes;
+  k.qblobs = s->d_qblobs; k.qblob_off = s->d_qoff; k.qblob_bytes = s->d_qbytes;
+  k.restarts = pp->restarts; k.lsoln = pp->lsoln; k.accept_mode = pp->accept_mode;
+  k.seed_lo = (uint32_t)seed; k.seed_hi = (uint32_t)(seed >> 32);
+  k.accept_tab = s->d_accept;
+  k.out_scores = s->d_scores; k.out_maps = pp->lsoln ? s->d_maps : nullptr; k.out_stride = std::max(1, D);
+  k.xw_states = s->d_xw; k.pool_list = s->d_pool_list; k.xw_blocks = s->d_xw_blocks;
+
+  if (r1 > r0) {
+    if (xorwow) {
+      if (!s->xw_ready || s->xw_seed != seed) { rc = sats_searcher_reset_xorwow(s, seed); if (rc) return rc; }
+      // pool positions in original file order (cudaSaTabsearch_kernel.cu:932 walks d_orders[] as loaded)
+      std::vector<int32_t> list;
+      for (int kpos = r0; kpos < r1; kpos++) list.push_back(kpos);
+      std::sort(list.begin(), list.end(), [&](int a, int b) { return s->file_rank[a] < s->file_rank[b]; });
+      int grid_count = pp->grid_count > 1 ? pp->grid_count : 1;
+      int grid_rank = grid_count > 1 ? pp->grid_rank : 0;
+      if (grid_rank < 0 || grid_rank >= grid_count) return sats_fail(SATS_ERR_ARG, "bad grid_rank %d of %d", grid_rank, grid_count);
+      std::vector<int32_t> blocks;
+      for (int b = 0; b < SATS_REF_GRID_BLOCKS; b++) if (b % grid_count == grid_rank) blocks.push_back(b);
+      CK(cudaStreamSynchronize(s->stream));
+      CK(cudaMemcpy(s->d_pool_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(s->d_xw_blocks, blocks.data(), blocks.size() * 4, cudaMemcpyHostToDevice));
+      const int n2max = s->sorted_order[r0];
+      k.pool_count = (int)list.size();
+      k.tw = SATS_REF_GRID_THREADS; k.teams = 1;
+      k.sm_entry_bytes = (int)entry_blob_bytes(n2max);
+      for (int q = 0; q < Q; q++) {    // one launch per query, in order: the streams carry over
+        const int n1 = s->q_n1[q];
+        k.q_first = q;
+        k.sm_query_bytes = (int)s->q_bytes[q];
+        k.sm_mapwords = (n1 + 3) / 4;
+        k.sm_team_bytes = (int)round16(k.sm_entry_bytes + (size_t)k.sm_mapwords * k.tw * 4 * (pp->lsoln ? 2 : 1) + 64);
+        size_t smem = 16 + k.sm_query_bytes + k.sm_team_bytes;
+        if (smem > (size_t)kMaxSmem) return sats_fail(SATS_ERR_ARG, "query %d x entry order %d needs %zu B of shared memory", q, n2max, smem);
+        kernel_fn fn = pick_kernel(words_for(n1), words_for(n2max), pp->lorder != 0, true);
+        fn<<<dim3((unsigned)blocks.size(), 1), k.tw, smem, s->stream>>>(k);
+        CK(cudaGetLastError());
+        s->launches++;
+      }
+    } else {
+      const int tw = std::min(128, ((pp->restarts + 31) / 32) * 32);
+      k.tw = tw;
+      // runs of consecutive queries with the same mask width share launches (grid.y)
+      for (int q0 = 0; q0 < Q;) {
+        int q1 = q0 + 1;
+        const int w1 = words_for(s->q_n1[q0]);
+        while (q1 < Q && words_for(s->q_n1[q1]) == w1) q1++;
+        int n1max = 0; uint32_t qbmax = 0;
+        for (int q = q0; q < q1; q++) { n1max = std::max(n1max, s->q_n1[q]); qbmax = std::max(qbmax, s->q_bytes[q]); }
+        k.q_first = q0;
+        k.sm_query_bytes = (int)qbmax;
+        k.sm_mapwords = (n1max + 3) / 4;
+        int b0 = r0;
+        while (b0 < r1) {
+          // bucket = maximal run of entries whose order falls under the same bound (list is decreasing)
+          const int n2max = s->sorted_order[b0];
+          int lowbound = 0;
+          for (int bb : kBucketBounds) { if (bb >= n2max) break; lowbound = bb; }
+          int b1 = b0;
+          while (b1 < r1 && s->sorted_order[b1] > lowbound) b1++;
+          k.sm_entry_bytes = (int)entry_blob_bytes(n2max);
+          k.sm_team_bytes = (int)round16(k.sm_entry_bytes + (size_t)k.sm_mapwords * tw * 4 * (pp->lsoln ? 2 : 1) + 64);
+          kernel_fn fn = pick_kernel(w1, words_for(n2max), pp->lorder != 0, false);
+          // teams per CTA: as many as fit while keeping the most warps resident per SM
+          int best_teams = 0, best_warps = -1;
+          for (int teams = 512 / tw; teams >= 1; teams >>= 1) {
+            size_t smem = 16 + k.sm_query_bytes + (size_t)teams * k.sm_team_bytes;
+            if (smem > (size_t)kMaxSmem) continue;
+            int ctas = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, fn, teams * tw, smem));
+            int warps = ctas * teams * tw / 32;
+            if (warps > best_warps) { best_warps = warps; best_teams = teams; }
+          }
+          if (best_teams == 0) return sats_fail(SATS_ERR_ARG, "query order %d x entry order %d does not fit in shared memory", n1max, n2max);
+          k.teams = best_teams;
+          k.item_first = b0; k.item_count = b1 - b0;
+          size_t smem = 16 + k.sm_query_bytes + (size_t)k.teams * k.sm_team_bytes;
+          dim3 grid((unsigned)((k.item_count + k.teams - 1) / k.teams), (unsigned)(q1 - q0));
+          fn<<<grid, k.teams * tw, smem, s->stream>>>(k);
+          CK(cudaGetLastError());
+          s->launches++;
+          b0 = b1;
+        }
+        q0 = q1;
+      }
+    }
+  }
+  if (elapsed_ms) {
+    CK(cudaEventRecord(s->ev1, s->stream));
+    CK(cudaEventSynchronize(s->ev1));
+    CK(cudaEventElapsedTime(elapsed_ms, s->ev0, s->ev1));
+  }
+  return SATS_OK;
+}
+
+extern "C" int sats_search_collect(sats_searcher *s, int32_t *scores, int32_t *maps)
+{
+  if (!s || !scores) return sats_fail(SATS_ERR_ARG, "sats_search_collect: null argument");
+  if (s->last_lsoln && !maps) return sats_fail(SATS_ERR_ARG, "sats_search_collect: maps buffer required with lsoln");
+  CK(cudaSetDevice(s->device));
+  const int D = (int)s->sorted_orig.size(), Q = s->last_q;
+  if (D == 0) return SATS_OK;
+  size_t n = (size_t)Q * D;
+  CK(cudaMemcpyAsync(s->h_scores, s->d_scores, n * 4, cudaMemcpyDeviceToHost, s->stream));
+  if (s->last_lsoln) CK(cudaMemcpyAsync(s->h_maps, s->d_maps, n * SATS_K_MAPROW, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  for (int q = 0; q < Q; q++) {
+    const int n1 = s->q_n1[q];
+    for (int kpos = 0; kpos < D; kpos++) {
+      int v = s->h_scores[(size_t)q * D + kpos];
+      if (v == kScoreSentinel) continue;
+      size_t o = (size_t)q * s->db_count + s->sorted_orig[kpos];
+      scores[o] = v;
+      if (s->last_lsoln) {
+        const int8_t *row = s->h_maps + ((size_t)q * D + kpos) * SATS_K_MAPROW;
+        int32_t *dst = maps + o * SATS_MAP_STRIDE;
+        for (int i = 0; i < n1; i++) dst[i] = row[i];
+      }
+    }
+  }
+  return SATS_OK;
+}
+
+extern "C" int sats_search(sats_searcher *s, const sats_db *queries, int qfirst, int qcount, const sats_params *params,
+                           uint32_t query_index_base, int32_t *scores, int32_t *maps)
+{
+  int rc = sats_search_upload(s, queries, qfirst, qcount);
+  if (rc) return rc;
+  rc = sats_search_launch(s, params, query_index_base, nullptr);
+  if (rc) return rc;
+  return sats_search_collect(s, scores, maps);
+}

@@ -1,0 +1,536 @@
+// sats_host.cpp -- host half of libsats: structure parsing, database container, file formats,
+// Gumbel statistics, result formatting, sharding.  No CUDA here.
+//
+// Behaviour follows the reference's host libraries (stivalaa/cuda_satabsearch, nvcc_src_current/):
+//   parsetableaux.c:52-138   SSE-type and tableau-code encodings
+//   parsetableaux.c:193-294  row grammar of tableau / distance-matrix blocks (3- and 7-column cells)
+//   parsetableaux.c:317-632  read_database / read_queries (header "%8s %d", oversize entries skipped)
+//   gumbelstats.c:50-94      norm2 / z_gumbel / pv_gumbel
+//   cudaSaTabsearch.cu:415-454, 631-693  output grammar, stdin grammar
+//   scripts/convdb2.py:182-231  ASCII database writer
+#include <algorithm>
+#include <cctype>
+#include <cerrno>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <strings.h>
+
+#include "sats_internal.h"
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+int sats_fail(int status, const char *fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return status;
+}
+
+extern "C" const char *sats_last_error(void) { return g_err; }
+extern "C" const char *sats_version(void) { return "cuda_satabsearch_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------ container
+void sats_db::append(const char *nm, int n, const uint8_t *tri_tab, const float *tri_dmat)
+{
+  if (tri_off.empty()) tri_off.push_back(0);
+  int64_t cells = (int64_t)n * (n + 1) / 2;
+  order.push_back(n);
+  char slot[9] = {0};
+  strncpy(slot, nm, SATS_LABELSIZE);
+  names.insert(names.end(), slot, slot + 9);
+  tab.insert(tab.end(), tri_tab, tri_tab + cells);
+  dmat.insert(dmat.end(), tri_dmat, tri_dmat + cells);
+  tri_off.push_back(tri_off.back() + cells);
+}
+
+// ------------------------------------------------------------------------------------------ parsing
+namespace {
+
+struct Cursor {
+  const char *p, *end;
+  bool eof() const { return p >= end; }
+  // next line without its terminator; false at end of text
+  bool line(const char *&b, const char *&e)
+  {
+    if (p >= end) return false;
+    b = p;
+    const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+    e = nl ? nl : end;
+    p = nl ? nl + 1 : end;
+    return true;
+  }
+  void skip_space()
+  {
+    while (p < end && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r' || *p == '\f' || *p == '\v')) p++;
+  }
+};
+
+int type_code(char c0, char c1, int *out)
+{
+  if (c0 == 'e') { *out = 0; return 0; }
+  switch (c1) {
+    case 'a': *out = 1; return 0;
+    case 'i': *out = 2; return 0;
+    case 'g': *out = 3; return 0;
+    default: return sats_fail(SATS_ERR_PARSE, "Bad helix type %c", c1);
+  }
+}
+
+int tableau_code(char c0, char c1, int *out)
+{
+  int hi, lo;
+  switch (c0) {
+    case 'P': hi = 0; break;
+    case 'R': hi = 1; break;
+    case 'O': hi = 2; break;
+    case 'L': hi = 3; break;
+    case '?': hi = 4; break;
+    default: return sats_fail(SATS_ERR_PARSE, "invalid tableaux code %c", c0);
+  }
+  switch (c1) {
+    case 'E': lo = 0; break;
+    case 'D': lo = 1; break;
+    case 'S': lo = 2; break;
+    case 'T': lo = 3; break;
+    case '?': lo = 4; break;
+    default: return sats_fail(SATS_ERR_PARSE, "invalid tableaux code %c", c1);
+  }
+  *out = (hi << 4) | lo;
+  return 0;
+}
+
+// header token pair "%8s %d": a name of at most 8 characters, then the order
+bool read_header(Cursor &c, char name[9], int *order)
+{
+  c.skip_space();
+  if (c.eof()) return false;
+  int k = 0;
+  while (c.p < c.end && k < 8 && !isspace((unsigned char)*c.p)) name[k++] = *c.p++;
+  name[k] = 0;
+  if (k == 0) return false;
+  c.skip_space();
+  if (c.eof()) return false;
+  char num[16];
+  int m = 0;
+  if (c.p < c.end && (*c.p == '-' || *c.p == '+')) num[m++] = *c.p++;
+  while (c.p < c.end && m < 15 && *c.p >= '0' && *c.p <= '9') num[m++] = *c.p++;
+  num[m] = 0;
+  if (m == 0 || (m == 1 && (num[0] == '-' || num[0] == '+'))) return false;
+  *order = atoi(num);
+  // the trailing "\n" of the reference's fscanf format eats the rest of the whitespace
+  while (c.p < c.end && (*c.p == ' ' || *c.p == '\t' || *c.p == '\r')) c.p++;
+  if (c.p < c.end && *c.p == '\n') c.p++;
+  return true;
+}
+
+// Parses consecutive entries until the text ends or a header fails to parse.
+int parse_entries(Cursor &c, const char *what, sats_db *db)
+{
+  std::vector<uint8_t> ttab;
+  std::vector<float> tdm;
+  int skipped = 0;
+  char name[9];
+  int n;
+  while (read_header(c, name, &n)) {
+    if (n < 1) return sats_fail(SATS_ERR_PARSE, "%s structure %s has bad order %d", what, name, n);
+    bool keep = n <= SATS_MAXDIM;
+    if (!keep) {
+      fprintf(stderr, "Tableau %s order %d is too large (max is %d)\n", name, n, SATS_MAXDIM);
+      fprintf(stderr, "WARNING: excluded %s structure %s as it is too large\n", what, name);
+      skipped++;
+    }
+    size_t cells = (size_t)n * (n + 1) / 2;
+    ttab.assign(cells, 0);
+    tdm.assign(cells, 0.f);
+    const char *b, *e;
+    for (int i = 0; i < n; i++) {
+      if (!c.line(b, e)) return sats_fail(SATS_ERR_PARSE, "%s structure %s: truncated tableau (row %d of %d)", what, name, i + 1, n);
+      if (!keep) continue;
+      if (e - b < 3 * i + 2) return sats_fail(SATS_ERR_PARSE, "%s structure %s: tableau row %d too short", what, name, i + 1);
+      for (int j = 0; j <= i; j++) {
+        int v, rc;
+        rc = (i == j) ? type_code(b[3 * j], b[3 * j + 1], &v) : tableau_code(b[3 * j], b[3 * j + 1], &v);
+        if (rc) return rc;
+        ttab[(size_t)i * (i + 1) / 2 + j] = (uint8_t)v;
+      }
+    }
+    char field[64];
+    for (int i = 0; i < n; i++) {
+      if (!c.line(b, e)) return sats_fail(SATS_ERR_PARSE, "%s structure %s: truncated distance matrix (row %d of %d)", what, name, i + 1, n);
+      if (!keep) continue;
+      for (int j = 0; j <= i; j++) {
+        // strtof(&buf[j*7]): conversion starts at column 7j and stops at the first character that
+        // cannot continue a number (so a wider value bleeds into the next field, as in the reference)
+        const char *s = b + 7 * j;
+        if (s >= e) return sats_fail(SATS_ERR_PARSE, "%s structure %s: distance row %d too short", what, name, i + 1);
+        size_t len = std::min((size_t)(e - s), sizeof field - 1);
+        memcpy(field, s, len);
+        field[len] = 0;
+        tdm[(size_t)i * (i + 1) / 2 + j] = strtof(field, nullptr);
+      }
+    }
+    if (keep) db->append(name, n, ttab.data(), tdm.data());
+  }
+  if (skipped) fprintf(stderr, "WARNING: skipped %d %s tableaux of order > %d\n", skipped, what, SATS_MAXDIM);
+  return 0;
+}
+
+int slurp(const char *path, std::string *out)
+{
+  FILE *fp = fopen(path, "rb");
+  if (!fp) return sats_fail(SATS_ERR_IO, "ERROR opening db file %s", path);
+  char buf[1 << 16];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof buf, fp)) > 0) out->append(buf, n);
+  fclose(fp);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int sats_db_parse_ascii(const char *text, size_t len, sats_db **out)
+{
+  if (!text || !out) return sats_fail(SATS_ERR_ARG, "sats_db_parse_ascii: null argument");
+  sats_db *db = new sats_db();
+  db->tri_off.push_back(0);
+  Cursor c{text, text + len};
+  int rc = parse_entries(c, "database", db);
+  if (rc) { delete db; return rc; }
+  *out = db;
+  return SATS_OK;
+}
+
+extern "C" int sats_db_read_ascii(const char *path, sats_db **out)
+{
+  if (!path || !out) return sats_fail(SATS_ERR_ARG, "sats_db_read_ascii: null argument");
+  std::string text;
+  int rc = slurp(path, &text);
+  if (rc) return rc;
+  return sats_db_parse_ascii(text.data(), text.size(), out);
+}
+
+extern "C" int sats_input_parse(const char *text, size_t len, char *dbfile, size_t dbfile_cap, int flags_tf[3],
+                                sats_db **queries)
+{
+  if (!text || !dbfile || !flags_tf || !queries || dbfile_cap < 2) return sats_fail(SATS_ERR_ARG, "sats_input_parse: bad argument");
+  Cursor c{text, text + len};
+  c.skip_space();
+  size_t k = 0;
+  while (c.p < c.end && !isspace((unsigned char)*c.p)) {
+    if (k + 1 < dbfile_cap) dbfile[k++] = *c.p;
+    c.p++;
+  }
+  dbfile[k] = 0;
+  if (k == 0) return sats_fail(SATS_ERR_PARSE, "ERROR reading dbfilename from stdin");
+  c.skip_space();
+  // "%c %c %c\n"
+  char f[3];
+  for (int i = 0; i < 3; i++) {
+    if (i) c.skip_space();
+    if (c.eof()) return sats_fail(SATS_ERR_PARSE, "ERROR reading options from stdin");
+    f[i] = *c.p++;
+  }
+  for (int i = 0; i < 3; i++) flags_tf[i] = (f[i] == 'T');
+  sats_db *q = new sats_db();
+  q->tri_off.push_back(0);
+  int rc = parse_entries(c, "query", q);
+  if (rc) { delete q; return rc; }
+  if (q->count() == 0) { delete q; return sats_fail(SATS_ERR_PARSE, "ERROR: no query structures found on stdin"); }
+  *queries = q;
+  return SATS_OK;
+}
+
+extern "C" int sats_idlist_parse(const char *text, size_t len, char *ids_out, int max_ids)
+{
+  if (!text || !ids_out) return sats_fail(SATS_ERR_ARG, "sats_idlist_parse: null argument");
+  Cursor c{text, text + len};
+  const char *b, *e;
+  int n = 0;
+  while (c.line(b, e)) {
+    while (e > b && (e[-1] == '\r')) e--;
+    if (e == b) continue;               // blank line (the reference would fail on it later)
+    if (n >= max_ids) return sats_fail(SATS_ERR_ARG, "too many query ids (max %d)", max_ids);
+    char *slot = ids_out + (size_t)n * 9;
+    memset(slot, 0, 9);
+    size_t k = std::min((size_t)(e - b), (size_t)(SATS_LABELSIZE - 1));   // queryptr[LABELSIZE-1] = '\0'
+    memcpy(slot, b, k);
+    n++;
+  }
+  return n;
+}
+
+extern "C" int sats_db_from_arrays(int count, const int32_t *order, const char *names, const int64_t *off,
+                                   const uint8_t *tabs, const float *dmats, sats_db **out)
+{
+  if (count < 0 || !out || (count && (!order || !names || !off || !tabs || !dmats)))
+    return sats_fail(SATS_ERR_ARG, "sats_db_from_arrays: bad argument");
+  sats_db *db = new sats_db();
+  db->tri_off.push_back(0);
+  std::vector<uint8_t> tt;
+  std::vector<float> td;
+  for (int e = 0; e < count; e++) {
+    int n = order[e];
+    if (n < 1 || n > SATS_MAXDIM) { delete db; return sats_fail(SATS_ERR_ARG, "entry %d has order %d outside 1..%d", e, n, SATS_MAXDIM); }
+    tt.resize((size_t)n * (n + 1) / 2);
+    td.resize(tt.size());
+    const uint8_t *t = tabs + off[e];
+    const float *d = dmats + off[e];
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j <= i; j++) {
+        tt[(size_t)i * (i + 1) / 2 + j] = t[(size_t)i * n + j];
+        td[(size_t)i * (i + 1) / 2 + j] = d[(size_t)i * n + j];
+      }
+    char nm[9] = {0};
+    memcpy(nm, names + (size_t)e * 9, 8);
+    db->append(nm, n, tt.data(), td.data());
+  }
+  *out = db;
+  return SATS_OK;
+}
+
+extern "C" void sats_db_free(sats_db *db) { delete db; }
+extern "C" int sats_db_count(const sats_db *db) { return db ? db->count() : 0; }
+extern "C" int sats_db_order(const sats_db *db, int i) { return (db && i >= 0 && i < db->count()) ? db->order[i] : SATS_ERR_ARG; }
+extern "C" const char *sats_db_name(const sats_db *db, int i) { return (db && i >= 0 && i < db->count()) ? db->name(i) : ""; }
+
+extern "C" int sats_db_max_order(const sats_db *db)
+{
+  int m = 0;
+  if (db) for (int n : db->order) m = std::max(m, n);
+  return m;
+}
+
+extern "C" int sats_db_get(const sats_db *db, int e, uint8_t *tab, float *dmat)
+{
+  if (!db || e < 0 || e >= db->count()) return sats_fail(SATS_ERR_ARG, "sats_db_get: bad index %d", e);
+  int n = db->order[e];
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) {
+      if (tab) tab[(size_t)i * n + j] = db->code(e, i, j);
+      if (dmat) dmat[(size_t)i * n + j] = db->dist(e, i, j);
+    }
+  return SATS_OK;
+}
+
+extern "C" int sats_db_find(const sats_db *db, const char *name)
+{
+  if (!db || !name) return sats_fail(SATS_ERR_ARG, "sats_db_find: null argument");
+  for (int i = 0; i < db->count(); i++)
+    if (!strcasecmp(name, db->name(i))) return i;
+  return sats_fail(SATS_ERR_NOTFOUND, "ERROR: query %s not found", name);
+}
+
+extern "C" int sats_db_select(const sats_db *src, const int32_t *index, int count, sats_db **out)
+{
+  if (!src || !out || count < 0 || (count && !index)) return sats_fail(SATS_ERR_ARG, "sats_db_select: bad argument");
+  sats_db *db = new sats_db();
+  db->tri_off.push_back(0);
+  for (int k = 0; k < count; k++) {
+    int e = index[k];
+    if (e < 0 || e >= src->count()) { delete db; return sats_fail(SATS_ERR_ARG, "sats_db_select: bad index %d", e); }
+    db->append(src->name(e), src->order[e], src->tab.data() + src->tri_off[e], src->dmat.data() + src->tri_off[e]);
+  }
+  *out = db;
+  return SATS_OK;
+}
+
+extern "C" int sats_db_bootstrap(const sats_db *src, int count, uint64_t seed, int sort_by_order, sats_db **out)
+{
+  if (!src || !out || count < 0 || src->count() == 0) return sats_fail(SATS_ERR_ARG, "sats_db_bootstrap: bad argument");
+  uint64_t x = seed ? seed : 0x9E3779B97F4A7C15ull;
+  std::vector<int32_t> pick((size_t)count);
+  for (int k = 0; k < count; k++) {
+    x ^= x >> 12; x ^= x << 25; x ^= x >> 27;              // xorshift64*
+    uint64_t r = x * 0x2545F4914F6CDD1Dull;
+    pick[k] = (int32_t)((r >> 33) % (uint64_t)src->count());
+  }
+  std::vector<int32_t> pos((size_t)count);
+  std::iota(pos.begin(), pos.end(), 0);
+  if (sort_by_order)
+    std::stable_sort(pos.begin(), pos.end(), [&](int a, int b) { return src->order[pick[a]] < src->order[pick[b]]; });
+  sats_db *db = new sats_db();
+  db->tri_off.push_back(0);
+  char nm[16];
+  for (int k = 0; k < count; k++) {
+    int e = pick[pos[k]];
+    snprintf(nm, sizeof nm, "s%06d", pos[k] % 1000000);
+    db->append(nm, src->order[e], src->tab.data() + src->tri_off[e], src->dmat.data() + src->tri_off[e]);
+  }
+  *out = db;
+  return SATS_OK;
+}
+
+// ------------------------------------------------------------------------------------------ writers
+extern "C" int sats_db_write_ascii(const sats_db *db, const char *path)
+{
+  if (!db || !path) return sats_fail(SATS_ERR_ARG, "sats_db_write_ascii: null argument");
+  FILE *fp = fopen(path, "w");
+  if (!fp) return sats_fail(SATS_ERR_IO, "cannot open %s for writing", path);
+  static const char HI[] = "PROL?", LO[] = "EDST?";
+  static const char *TY[] = {"e ", "xa", "xi", "xg"};
+  for (int e = 0; e < db->count(); e++) {
+    int n = db->order[e];
+    if (e) fputc('\n', fp);
+    fprintf(fp, "%6s %4d\n", db->name(e), n);
+    for (int i = 0; i < n; i++) {
+      for (int j = 0; j <= i; j++) {
+        uint8_t v = db->code(e, i, j);
+        if (i == j) fprintf(fp, "%s ", TY[v & 3]);
+        else fprintf(fp, "%c%c ", HI[std::min(v >> 4, 4)], LO[std::min(v & 15, 4)]);
+      }
+      fputc('\n', fp);
+    }
+    for (int i = 0; i < n; i++) {
+      for (int j = 0; j <= i; j++) {
+        float d = db->dist(e, i, j);
+        fprintf(fp, "%6.3f ", std::isnan(d) ? 0.0 : (double)d);      // convdb2.py: NaN -> 0.000
+      }
+      fputc('\n', fp);
+    }
+  }
+  if (fclose(fp)) return sats_fail(SATS_ERR_IO, "write error on %s", path);
+  return SATS_OK;
+}
+
+static const char PACKED_MAGIC[8] = {'S', 'A', 'T', 'S', 'D', 'B', '1', 0};
+
+extern "C" int sats_db_write_packed(const sats_db *db, const char *path)
+{
+  if (!db || !path) return sats_fail(SATS_ERR_ARG, "sats_db_write_packed: null argument");
+  FILE *fp = fopen(path, "wb");
+  if (!fp) return sats_fail(SATS_ERR_IO, "cannot open %s for writing", path);
+  uint32_t count = (uint32_t)db->count(), zero = 0;
+  uint64_t cells = (uint64_t)db->tab.size();
+  static const char pad[8] = {0};
+  fwrite(PACKED_MAGIC, 1, 8, fp);
+  fwrite(&count, 4, 1, fp); fwrite(&zero, 4, 1, fp); fwrite(&cells, 8, 1, fp);
+  fwrite(db->order.data(), 4, count, fp);
+  fwrite(db->names.data(), 1, (size_t)count * 9, fp);
+  fwrite(pad, 1, (8 - (13 * (size_t)count) % 8) % 8, fp);
+  fwrite(db->tab.data(), 1, cells, fp);
+  fwrite(pad, 1, (8 - cells % 8) % 8, fp);
+  fwrite(db->dmat.data(), 4, cells, fp);
+  if (fclose(fp)) return sats_fail(SATS_ERR_IO, "write error on %s", path);
+  return SATS_OK;
+}
+
+extern "C" int sats_db_read_packed(const char *path, sats_db **out)
+{
+  if (!path || !out) return sats_fail(SATS_ERR_ARG, "sats_db_read_packed: null argument");
+  std::string raw;
+  int rc = slurp(path, &raw);
+  if (rc) return rc;
+  if (raw.size() < 24 || memcmp(raw.data(), PACKED_MAGIC, 8)) return sats_fail(SATS_ERR_PARSE, "%s is not a SATSDB1 file", path);
+  uint32_t count; uint64_t cells;
+  memcpy(&count, raw.data() + 8, 4);
+  memcpy(&cells, raw.data() + 16, 8);
+  size_t pos = 24;
+  size_t need = pos + 13 * (size_t)count + (8 - (13 * (size_t)count) % 8) % 8 + cells + (8 - cells % 8) % 8 + 4 * cells;
+  if (raw.size() < need) return sats_fail(SATS_ERR_PARSE, "%s is truncated", path);
+  sats_db *db = new sats_db();
+  db->order.resize(count);
+  memcpy(db->order.data(), raw.data() + pos, 4 * (size_t)count); pos += 4 * (size_t)count;
+  db->names.assign(raw.data() + pos, raw.data() + pos + 9 * (size_t)count); pos += 9 * (size_t)count;
+  pos += (8 - (13 * (size_t)count) % 8) % 8;
+  db->tab.assign((const uint8_t *)raw.data() + pos, (const uint8_t *)raw.data() + pos + cells); pos += cells + (8 - cells % 8) % 8;
+  db->dmat.resize(cells);
+  memcpy(db->dmat.data(), raw.data() + pos, 4 * cells);
+  db->tri_off.assign(1, 0);
+  uint64_t sum = 0;
+  for (uint32_t e = 0; e < count; e++) {
+    int n = db->order[e];
+    if (n < 1 || n > SATS_MAXDIM) { delete db; return sats_fail(SATS_ERR_PARSE, "%s: entry %u has order %d", path, e, n); }
+    sum += (uint64_t)n * (n + 1) / 2;
+    db->tri_off.push_back((int64_t)sum);
+  }
+  if (sum != cells) { delete db; return sats_fail(SATS_ERR_PARSE, "%s: cell count mismatch", path); }
+  *out = db;
+  return SATS_OK;
+}
+
+// ------------------------------------------------------------------------------------------ statistics
+extern "C" {
+const double sats_gumbel_a = 0.3780327676087335;
+const double sats_gumbel_b = 0.3582596175507505;
+}
+static const double kEulerGamma = 0.5772156649015328606;
+
+extern "C" double sats_norm2(int score, int size1, int size2) { return 2.0 * score / ((double)(size1 + size2)); }
+
+extern "C" double sats_z_gumbel(int x, double a, double b)
+{
+  double mu = a + b * kEulerGamma;
+  double sigma = (M_PI / sqrt(6.0)) * b;
+  return (x - mu) / sigma;
+}
+
+extern "C" double sats_pv_gumbel(double z) { return 1 - exp(-exp(-((M_PI / sqrt(6.0)) * z + kEulerGamma))); }
+
+extern "C" size_t sats_format_block(char *buf, size_t cap, const char *query_id, int query_order, const char *dbfile,
+                                    int lorder, int lsoln, const sats_db *db, const int32_t *index, int count,
+                                    const int32_t *scores, const int32_t *maps)
+{
+  size_t used = 0;
+  auto emit = [&](const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    int n = vsnprintf(used < cap ? buf + used : nullptr, used < cap ? cap - used : 0, fmt, ap);
+    va_end(ap);
+    if (n > 0) used += (size_t)n;
+  };
+  emit("# cudaSaTabsearch LTYPE = %c LORDER = %c LSOLN = %c\n", 'T', lorder ? 'T' : 'F', lsoln ? 'T' : 'F');
+  emit("# QUERY ID = %-8s\n", query_id);
+  emit("# DBFILE = %-80s\n", dbfile);
+  for (int k = 0; k < count; k++) {
+    int e = index ? index[k] : k;
+    double n2s = sats_norm2(scores[e], query_order, db->order[e]);
+    double z = sats_z_gumbel((int)n2s, sats_gumbel_a, sats_gumbel_b);   // implicit double -> int at the call, as in the reference
+    double pv = sats_pv_gumbel(z);
+    emit("%-8s %d %g %g %g\n", db->name(e), scores[e], n2s, z, pv);
+    if (lsoln && maps)
+      for (int i = 0; i < query_order; i++) {
+        int j = maps[(size_t)e * SATS_MAP_STRIDE + i];
+        if (j >= 0) emit("%3d %3d\n", i + 1, j + 1);
+      }
+  }
+  return used;
+}
+
+// ------------------------------------------------------------------------------------------ sharding
+extern "C" int sats_partition(const sats_db *db, int shard_count, int32_t *owner)
+{
+  if (!db || !owner || shard_count < 1) return sats_fail(SATS_ERR_ARG, "sats_partition: bad argument");
+  int n = db->count();
+  std::vector<int32_t> idx((size_t)n);
+  std::iota(idx.begin(), idx.end(), 0);
+  std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return db->order[a] > db->order[b]; });
+  std::vector<double> load((size_t)shard_count, 0.0);
+  for (int k = 0; k < n; k++) {     // longest-processing-time-first over the size-sorted list
+    int best = 0;
+    for (int s = 1; s < shard_count; s++)
+      if (load[s] < load[best]) best = s;
+    owner[idx[k]] = best;
+    load[best] += sats_entry_cost(db->order[idx[k]]);
+  }
+  return SATS_OK;
+}
+
+extern "C" void sats_params_default(sats_params *p)
+{
+  if (!p) return;
+  memset(p, 0, sizeof *p);
+  p->lorder = 1;
+  p->lsoln = 0;
+  p->restarts = SATS_DEFAULT_MAXSTART;
+  p->rng_mode = SATS_RNG_PHILOX;
+  p->accept_mode = SATS_ACCEPT_HOST_TABLE;
+  p->pool = SATS_POOL_ALL;
+  p->pool_threshold = SATS_MAXDIM_GPU;
+  p->seed = SATS_REF_SEED;
+}

@@ -1,0 +1,552 @@
+// sats_kernel.cuh -- the simulated-annealing tableau-search kernel for sm_100a.
+//
+// Replaces the body of sa_tabsearch_gpu (reference nvcc_src_current/cudaSaTabsearch_kernel.cu:804-1236)
+// and its helpers tscord (:306), tmscord (:396), deltasd (:502), thinit (:588), randtypeind (:677).
+// It is a new design, not a translation:
+//
+//   * One LANE runs one restart chain.  A TEAM of TW (32/64/128) threads shares one database entry and
+//     covers `restarts` chains in rounds of TW; a CTA holds several teams (several entries) that share one
+//     copy of the query.  Teams synchronise with named barriers only.
+//   * The query blob and every team's entry blob are brought into shared memory by TMA 1-D bulk copies
+//     (cp.async.bulk ... mbarrier::complete_tx) issued by one thread; everybody waits on the mbarrier.
+//   * Chain state is bit masks in registers (mapped query SSEs, occupied entry SSEs) plus a byte map in
+//     lane-private, bank-conflict-free shared memory.  The LORDER window and the candidate list of the
+//     reference (linear scans, kernel.cu:1053-1083, :677-714) become O(1) mask arithmetic: clz/ffs for the
+//     neighbouring mapped SSEs, (type mask & ~occupied & range mask) for the candidates, popc/select-nth
+//     for the random pick.  deltasd walks only the *mapped* SSEs (set bits), reading one 8-byte
+//     {distance, code} cell per term.
+//   * Metropolis thresholds come from a host-built table of the reference's exact fp32 values
+//     expf((float)delta / T_m) (kernel.cu:1166) or, in DEVICE_FAST mode, from the same fast-math
+//     intrinsics the reference's GPU build uses.
+//   * Uniforms: Philox4x32-10 at static positions (production) or the reference's XORWOW grid streams
+//     consumed in the reference's order (validation).
+//   * Restart arg-max: redux.sync / ballot inside each warp, then across the team's warps through shared
+//     memory, with the reference's tie-break (kernel.cu:1205-1221).
+#ifndef SATS_KERNEL_CUH
+#define SATS_KERNEL_CUH
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define SATS_K_MOVES 100
+#define SATS_K_DCLAMP 229          // expf(-d/T) <= 2^-33 (smallest uniform) for every d >= 229 and T <= 10
+#define SATS_K_NEG_INIT (-99999)
+#define SATS_K_ENTRY_HDR 80        // 16 B header + 4 types x 4 words of type masks
+#define SATS_K_QUERY_HDR 128       // 16 B header + 112 B of SSE types
+#define SATS_K_MAPROW 112          // bytes per (query, entry) row of the device map output
+
+struct SatsKParams {
+  // database (this GPU's shard), entries sorted by decreasing order
+  const uint8_t *blobs;            // entry blobs, each 16-byte aligned
+  const uint64_t *blob_off;        // byte offset of entry k
+  const uint32_t *blob_bytes;      // size of entry k's blob (multiple of 16)
+  // queries of this launch: blockIdx.y selects one
+  const uint8_t *qblobs;
+  const uint64_t *qblob_off;
+  const uint32_t *qblob_bytes;
+  int q_first;                     // index into qblob_* of blockIdx.y == 0
+  // work: Philox -> entries [item_first, item_first + item_count) of the sorted list, `teams` per CTA
+  //       XORWOW -> CTA c is reference block xw_blocks[c]; it walks pool_list[b], pool_list[b+128], ...
+  int item_first, item_count;
+  const int32_t *pool_list;        // XORWOW: pool position -> sorted entry index
+  int pool_count;
+  const int32_t *xw_blocks;
+  uint32_t *xw_states;             // 16384 x 6 words (d, v0..v4)
+  // geometry / shared-memory carve-up (bytes)
+  int tw;                          // threads per team
+  int teams;                       // teams per CTA
+  int sm_query_bytes;              // room for the largest query blob of this launch
+  int sm_entry_bytes;              // room for the largest entry blob of this launch
+  int sm_mapwords;                 // 32-bit words per chain byte-map (ceil(n1max / 4))
+  int sm_team_bytes;               // total per team
+  // search parameters
+  int restarts, lsoln, accept_mode;
+  uint32_t seed_lo, seed_hi;
+  const float *accept_tab;         // [SATS_K_MOVES][SATS_K_DCLAMP + 1]
+  // outputs, indexed [query slot][sorted entry index]
+  int32_t *out_scores;
+  int8_t *out_maps;                // rows of SATS_K_MAPROW bytes, or nullptr
+  int out_stride;                  // entries per query slot
+};
+
+__constant__ float c_sats_temps[SATS_K_MOVES];   // T_m = 10 * 0.95^m accumulated in fp32 like kernel.cu:1189
+
+namespace satsk {
+
+// ------------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t arrivals)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  uint32_t done;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void team_sync(int team, int tw)
+{
+  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(tw) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ bit sets
+template <int W> __device__ __forceinline__ bool bit_test(const uint32_t (&m)[W], int b)
+{
+  uint32_t word = m[0];
+#pragma unroll
+  for (int w = 1; w < W; w++) if ((b >> 5) == w) word = m[w];
+  return (word >> (b & 31)) & 1u;
+}
+template <int W> __device__ __forceinline__ void bit_set(uint32_t (&m)[W], int b)
+{
+#pragma unroll
+  for (int w = 0; w < W; w++) if (W == 1 || (b >> 5) == w) m[w] |= 1u << (b & 31);
+}
+template <int W> __device__ __forceinline__ void bit_clear(uint32_t (&m)[W], int b)
+{
+#pragma unroll
+  for (int w = 0; w < W; w++) if (W == 1 || (b >> 5) == w) m[w] &= ~(1u << (b & 31));
+}
+// mask of bit positions < x within one word (x may be <= 0 or >= 32)
+__device__ __forceinline__ uint32_t below(int x) { return x <= 0 ? 0u : (x >= 32 ? 0xffffffffu : ((1u << x) - 1u)); }
+
+// highest set bit with index <= i, or -1
+template <int W> __device__ __forceinline__ int top_at_or_below(const uint32_t (&m)[W], int i)
+{
+  int r = -1;
+#pragma unroll
+  for (int w = 0; w < W; w++) {
+    uint32_t x = m[w] & below(i + 1 - 32 * w);
+    if (x) r = 32 * w + 31 - __clz(x);
+  }
+  return r;
+}
+// lowest set bit with index >= i, or -1
+template <int W> __device__ __forceinline__ int low_at_or_above(const uint32_t (&m)[W], int i)
+{
+  int r = -1;
+#pragma unroll
+  for (int w = W - 1; w >= 0; w--) {
+    uint32_t x = m[w] & ~below(i - 32 * w);
+    if (x) r = 32 * w + __ffs(x) - 1;
+  }
+  return r;
+}
+// index of the idx-th (0-based) set bit; idx < popcount
+template <int W> __device__ __forceinline__ int select_nth(const uint32_t (&c)[W], int idx)
+{
+  uint32_t word = c[0];
+  int base = 0;
+  if (W > 1) {
+    bool found = false;
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+      int pc = __popc(c[w]);
+      if (!found) {
+        if (idx < pc) { word = c[w]; base = 32 * w; found = true; }
+        else idx -= pc;
+      }
+    }
+  }
+  for (; idx > 0; idx--) word &= word - 1u;
+  return base + __ffs(word) - 1;
+}
+
+// ------------------------------------------------------------------------------------------------ uniforms
+__device__ __forceinline__ float unit_from_bits(uint32_t x)
+{
+  // cuRAND's _curand_uniform: (0, 1]; the product with 2^-32 is exact so FMA contraction cannot change it
+  return (float)x * 2.3283064e-10f + 1.1641532e-10f;
+}
+// (u - 1.1e-7) * n in double, truncated (kernel.cu:67, :1042, :710)
+__device__ __forceinline__ int scaled_index(float u, int n)
+{
+  double x = ((double)u - 1.1e-7) * (double)n;
+  return x <= 0.0 ? 0 : (int)x;
+}
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1, uint32_t (&out)[4])
+{
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct Xorwow {
+  uint32_t d, v0, v1, v2, v3, v4;
+  __device__ __forceinline__ void load(const uint32_t *p) { d = p[0]; v0 = p[1]; v1 = p[2]; v2 = p[3]; v3 = p[4]; v4 = p[5]; }
+  __device__ __forceinline__ void store(uint32_t *p) const { p[0] = d; p[1] = v0; p[2] = v1; p[3] = v2; p[4] = v3; p[5] = v4; }
+  __device__ __forceinline__ float next()
+  {
+    uint32_t t = v0 ^ (v0 >> 2);
+    v0 = v1; v1 = v2; v2 = v3; v3 = v4;
+    v4 = (v4 ^ (v4 << 4)) ^ (t ^ (t << 1));
+    d += 362437u;
+    return unit_from_bits(v4 + d);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ scoring
+__device__ __forceinline__ int zeta(uint32_t a, uint32_t b)
+{
+  uint32_t x = a ^ b;
+  int hits = ((x & 0xF0u) == 0u) + ((x & 0x0Fu) == 0u);
+  return hits ? hits : -2;
+}
+__device__ __forceinline__ int gated(uint2 q, uint2 e)
+{
+  float gap = fabsf(__uint_as_float(q.x) - __uint_as_float(e.x));
+  return gap <= 4.0f ? zeta(q.y, e.y) : 0;
+}
+
+// Per-team view of shared memory
+struct TeamView {
+  const uint2 *qcell;      // n1 x n1 {distance bits, code}
+  const uint8_t *qtype;    // n1
+  const uint2 *ecell;      // n2 x n2
+  const uint32_t *tmask;   // [4][4] type -> 128-bit mask of entry SSEs of that type
+  uint8_t *smap;           // this lane's byte map: byte k at smap[((k >> 2) * tw) * 4 + (k & 3)]
+  uint8_t *bmap;           // best map, same addressing
+  int n1, n2, tw, mapwords;
+};
+
+__device__ __forceinline__ uint8_t map_get(const uint8_t *m, int k, int tw) { return m[(((k >> 2) * tw) << 2) + (k & 3)]; }
+__device__ __forceinline__ void map_put(uint8_t *m, int k, int tw, uint8_t v) { m[(((k >> 2) * tw) << 2) + (k & 3)] = v; }
+
+template <int W1, int W2, bool LORDER, bool XORWOW>
+struct Chain {
+  uint32_t mq[W1];   // query SSEs currently mapped
+  uint32_t md[W2];   // entry SSEs currently occupied
+  int score;
+
+  // thinit (kernel.cu:588-648): walk the query, with probability 1/2 match SSE i to the next entry SSE of its type
+  template <class Draw> __device__ __forceinline__ void seed(const TeamView &v, Draw &&draw)
+  {
+#pragma unroll
+    for (int w = 0; w < W1; w++) mq[w] = 0u;
+#pragma unroll
+    for (int w = 0; w < W2; w++) md[w] = 0u;
+    for (int w = 0; w < v.mapwords; w++) reinterpret_cast<uint32_t *>(v.smap)[w * v.tw] = 0xffffffffu;
+    int next_j = 0;
+    for (int i = 0; i < v.n1; i++) {
+      float u = draw(i);
+      if (u < 0.5f) {
+        const uint32_t *tm = v.tmask + 4 * v.qtype[i];
+        uint32_t cand[W2];
+#pragma unroll
+        for (int w = 0; w < W2; w++) cand[w] = tm[w];
+        int j = low_at_or_above<W2>(cand, next_j);
+        if (j < 0) break;
+        map_put(v.smap, i, v.tw, (uint8_t)j);
+        bit_set<W1>(mq, i);
+        bit_set<W2>(md, j);
+        next_j = j + 1;
+      }
+    }
+  }
+
+  // tmscord (kernel.cu:396-440) over mapped pairs only
+  __device__ __forceinline__ int full_score(const TeamView &v) const
+  {
+    int total = 0;
+#pragma unroll
+    for (int wi = 0; wi < W1; wi++) {
+      uint32_t bi = mq[wi];
+      while (bi) {
+        int i = 32 * wi + __ffs(bi) - 1;
+        bi &= bi - 1u;
+        int j = map_get(v.smap, i, v.tw);
+        const uint2 *qrow = v.qcell + i * v.n1;
+        const uint2 *erow = v.ecell + j * v.n2;
+#pragma unroll
+        for (int wk = 0; wk < W1; wk++) {
+          if (wk < wi) continue;
+          uint32_t bk = mq[wk];
+          if (wk == wi) bk &= ~below((i & 31) + 1);
+          while (bk) {
+            int k = 32 * wk + __ffs(bk) - 1;
+            bk &= bk - 1u;
+            total += gated(qrow[k], erow[map_get(v.smap, k, v.tw)]);
+          }
+        }
+      }
+    }
+    return total;
+  }
+
+  // deltasd (kernel.cu:502-535) over mapped SSEs only
+  __device__ __forceinline__ int delta(const TeamView &v, int i, int from, int to) const
+  {
+    int d = 0;
+    const uint2 *qrow = v.qcell + i * v.n1;
+    const uint2 *frow = v.ecell + (from < 0 ? 0 : from) * v.n2;
+    const uint2 *trow = v.ecell + (to < 0 ? 0 : to) * v.n2;
+#pragma unroll
+    for (int w = 0; w < W1; w++) {
+      uint32_t b = mq[w];
+      if (W1 == 1 || (i >> 5) == w) b &= ~(1u << (i & 31));
+      while (b) {
+        int k = 32 * w + __ffs(b) - 1;
+        b &= b - 1u;
+        int l = map_get(v.smap, k, v.tw);
+        uint2 q = qrow[k];
+        if (from >= 0) d -= gated(q, frow[l]);
+        if (to >= 0) d += gated(q, trow[l]);
+      }
+    }
+    return d;
+  }
+
+  // One Metropolis move (kernel.cu:1032-1191).  u1/u2/u3 are callables so that a sequential generator
+  // is advanced exactly when the reference would draw (u2 only with >= 2 candidates).
+  template <class U1, class U2, class U3>
+  __device__ __forceinline__ void move(const TeamView &v, int m, const SatsKParams &p, int &best, int &best_tag, int tag,
+                                       U1 &&u1, U2 &&u2, U3 &&u3)
+  {
+    const int i = scaled_index(u1(), v.n1);
+    const bool was_mapped = bit_test<W1>(mq, i);
+    int lo, hi, from;
+    if (LORDER) {
+      int kp = top_at_or_below<W1>(mq, i);
+      lo = kp >= 0 ? (int)map_get(v.smap, kp, v.tw) : v.n2;
+      from = was_mapped ? lo : -1;
+      if (i == v.n1 - 1) hi = v.n2;
+      else {
+        int kn = low_at_or_above<W1>(mq, i + 1);
+        hi = kn >= 0 ? (int)map_get(v.smap, kn, v.tw) : -1;
+      }
+    } else {
+      lo = 0; hi = v.n2;
+      from = was_mapped ? (int)map_get(v.smap, i, v.tw) : -1;
+    }
+    // randtypeind (kernel.cu:677-714): unoccupied entry SSEs of the right type inside [lo, hi)
+    const uint32_t *tm = v.tmask + 4 * v.qtype[i];
+    uint32_t cand[W2];
+    int ncand = 0;
+#pragma unroll
+    for (int w = 0; w < W2; w++) {
+      cand[w] = tm[w] & ~md[w] & below(hi - 32 * w) & ~below(lo - 32 * w);
+      ncand += __popc(cand[w]);
+    }
+    int to = -1;
+    if (ncand == 1) to = select_nth<W2>(cand, 0);
+    else if (ncand > 1) to = select_nth<W2>(cand, scaled_index(u2(), ncand));
+
+    int d = 0;
+    if (from >= 0 || to >= 0) d = delta(v, i, from, to);
+    const int cand_score = score + d;
+    if (cand_score > best) {
+      best = cand_score;
+      best_tag = tag;
+      if (p.lsoln) {
+        for (int w = 0; w < v.mapwords; w++)
+          reinterpret_cast<uint32_t *>(v.bmap)[w * v.tw] = reinterpret_cast<const uint32_t *>(v.smap)[w * v.tw];
+        map_put(v.bmap, i, v.tw, (uint8_t)to);     // -1 -> 0xff
+      }
+    }
+    const float u = u3();
+    bool accept;
+    if (p.accept_mode == SATS_ACCEPT_DEVICE_FAST) {
+      accept = __expf(__fdividef((float)d, c_sats_temps[m])) > u;
+    } else if (d > 0) {
+      accept = true;
+    } else if (d == 0) {
+      accept = 1.0f > u;
+    } else {
+      int nd = -d;
+      accept = nd <= SATS_K_DCLAMP && __ldg(p.accept_tab + m * (SATS_K_DCLAMP + 1) + nd) > u;
+    }
+    if (accept) {
+      score = cand_score;
+      if (from >= 0) bit_clear<W2>(md, from);
+      if (to >= 0) { bit_set<W2>(md, to); bit_set<W1>(mq, i); }
+      else bit_clear<W1>(mq, i);
+      if (from >= 0 || to >= 0) map_put(v.smap, i, v.tw, (uint8_t)to);
+    }
+  }
+};
+
+// Runs every chain this thread owns for one (query, entry) pair, then the team arg-max and the output.
+template <int W1, int W2, bool LORDER, bool XORWOW>
+__device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamView &v, int team, int tl, uint64_t *red,
+                                             uint32_t entry_orig, uint32_t query_index, Xorwow &xw,
+                                             int out_slot, int entry_sorted)
+{
+  Chain<W1, W2, LORDER, XORWOW> ch;
+  int best = SATS_K_NEG_INIT;
+  int best_tag = tl;                                  // XORWOW: thread id; Philox: restart index of the best chain
+  const int chains = XORWOW ? ((p.restarts + p.tw - 1) / p.tw) * p.tw : p.restarts;
+
+  for (int r = tl; r < chains; r += p.tw) {
+    const int tag = XORWOW ? tl : r;
+    if (XORWOW) {
+      ch.seed(v, [&](int) { return xw.next(); });
+    } else {
+      uint32_t rb[4];
+      int have = -1;
+      ch.seed(v, [&](int i) {
+        if ((i >> 2) != have) {
+          have = i >> 2;
+          philox4x32_10(0x80000000u | (uint32_t)have, (uint32_t)r, entry_orig, query_index, p.seed_lo, p.seed_hi, rb);
+        }
+        uint32_t x = rb[0];
+        if ((i & 3) == 1) x = rb[1];
+        if ((i & 3) == 2) x = rb[2];
+        if ((i & 3) == 3) x = rb[3];
+        return unit_from_bits(x);
+      });
+    }
+    ch.score = ch.full_score(v);
+    if (ch.score > best) {
+      best = ch.score;
+      best_tag = tag;
+      if (p.lsoln)
+        for (int w = 0; w < v.mapwords; w++)
+          reinterpret_cast<uint32_t *>(v.bmap)[w * v.tw] = reinterpret_cast<const uint32_t *>(v.smap)[w * v.tw];
+    }
+    if (XORWOW) {
+      for (int m = 0; m < SATS_K_MOVES; m++)
+        ch.move(v, m, p, best, best_tag, tag, [&] { return xw.next(); }, [&] { return xw.next(); }, [&] { return xw.next(); });
+    } else {
+      // static draw positions: move m, slot s -> draw 3m + s; four moves consume three Philox blocks
+      for (int g = 0; g < SATS_K_MOVES / 4; g++) {
+        uint32_t a[4], b[4], c[4];
+        philox4x32_10(3u * g + 0u, (uint32_t)r, entry_orig, query_index, p.seed_lo, p.seed_hi, a);
+        philox4x32_10(3u * g + 1u, (uint32_t)r, entry_orig, query_index, p.seed_lo, p.seed_hi, b);
+        philox4x32_10(3u * g + 2u, (uint32_t)r, entry_orig, query_index, p.seed_lo, p.seed_hi, c);
+        const int m = 4 * g;
+        ch.move(v, m + 0, p, best, best_tag, tag, [&] { return unit_from_bits(a[0]); }, [&] { return unit_from_bits(a[1]); }, [&] { return unit_from_bits(a[2]); });
+        ch.move(v, m + 1, p, best, best_tag, tag, [&] { return unit_from_bits(a[3]); }, [&] { return unit_from_bits(b[0]); }, [&] { return unit_from_bits(b[1]); });
+        ch.move(v, m + 2, p, best, best_tag, tag, [&] { return unit_from_bits(b[2]); }, [&] { return unit_from_bits(b[3]); }, [&] { return unit_from_bits(c[0]); });
+        ch.move(v, m + 3, p, best, best_tag, tag, [&] { return unit_from_bits(c[1]); }, [&] { return unit_from_bits(c[2]); }, [&] { return unit_from_bits(c[3]); });
+      }
+    }
+  }
+
+  // ---- arg-max over the team: highest score, lowest tag (kernel.cu:1205-1221 scans thread 0..127 with '>')
+  const unsigned full = 0xffffffffu;
+  int wbest = __reduce_max_sync(full, best);
+  unsigned wtag = __reduce_min_sync(full, best == wbest ? (unsigned)best_tag : 0xffffffffu);
+  const int warp_in_team = tl >> 5, warps = p.tw >> 5;
+  if ((tl & 31) == 0) red[warp_in_team] = ((uint64_t)(uint32_t)(wbest + 0x40000000) << 32) | (uint32_t)(~wtag);
+  team_sync(team, p.tw);
+  uint64_t key = red[0];
+  for (int w = 1; w < warps; w++) key = red[w] > key ? red[w] : key;
+  const int team_best = (int)(uint32_t)(key >> 32) - 0x40000000;
+  const unsigned team_tag = ~(uint32_t)key;
+  if (tl == 0) p.out_scores[(size_t)out_slot * p.out_stride + entry_sorted] = team_best;
+  if (p.lsoln && best == team_best && (unsigned)best_tag == team_tag) {
+    int8_t *row = p.out_maps + ((size_t)out_slot * p.out_stride + entry_sorted) * SATS_K_MAPROW;
+    for (int w = 0; w < v.mapwords; w++)
+      reinterpret_cast<uint32_t *>(row)[w] = reinterpret_cast<const uint32_t *>(v.bmap)[w * v.tw];
+  }
+  team_sync(team, p.tw);     // red[] and the entry buffer may be reused after this
+}
+
+}  // namespace satsk
+
+// Shared-memory layout of a CTA:
+//   [0,16)                      mbarrier
+//   [16, 16 + sm_query_bytes)   query blob
+//   then per team: entry blob (sm_entry_bytes) | byte maps (mapwords*tw*4) | best maps (same, if lsoln) | 64 B reduce scratch
+template <int W1, int W2, bool LORDER, bool XORWOW>
+__global__ void __launch_bounds__(512) sats_anneal_kernel(const SatsKParams p)
+{
+  using namespace satsk;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+  uint8_t *sq = smem + 16;
+  const int team = threadIdx.x / p.tw, tl = threadIdx.x - team * p.tw;
+  uint8_t *steam = smem + 16 + p.sm_query_bytes + (size_t)team * p.sm_team_bytes;
+  uint8_t *se = steam;
+  uint8_t *smaps = se + p.sm_entry_bytes;
+  const int mapbytes = p.sm_mapwords * p.tw * 4;
+  uint8_t *bmaps = smaps + mapbytes;
+  uint64_t *red = reinterpret_cast<uint64_t *>(bmaps + (p.lsoln ? mapbytes : 0));
+
+  const int qi = p.q_first + blockIdx.y;     // query slot of this batch: selects the blob and the output row
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+
+  TeamView v;
+  v.tw = p.tw;
+  v.mapwords = p.sm_mapwords;
+  v.qtype = sq + 16;
+  v.qcell = reinterpret_cast<const uint2 *>(sq + SATS_K_QUERY_HDR);
+  v.tmask = reinterpret_cast<const uint32_t *>(se + 16);
+  v.ecell = reinterpret_cast<const uint2 *>(se + SATS_K_ENTRY_HDR);
+  v.smap = smaps + tl * 4;
+  v.bmap = bmaps + tl * 4;
+  Xorwow xw;
+
+  if (!XORWOW) {
+    // one pass: team t anneals sorted entry item_first + blockIdx.x * teams + t
+    const int first = p.item_first + blockIdx.x * p.teams;
+    const int here = min(p.teams, p.item_first + p.item_count - first);
+    if (threadIdx.x == 0) {
+      uint32_t total = p.qblob_bytes[qi];
+      for (int t = 0; t < here; t++) total += p.blob_bytes[first + t];
+      mbar_expect_tx(bar, total);
+      tma_load_1d(sq, p.qblobs + p.qblob_off[qi], p.qblob_bytes[qi], bar);
+      for (int t = 0; t < here; t++)
+        tma_load_1d(smem + 16 + p.sm_query_bytes + (size_t)t * p.sm_team_bytes, p.blobs + p.blob_off[first + t],
+                    p.blob_bytes[first + t], bar);
+    }
+    mbar_wait(bar, 0);
+    if (team >= here) return;
+    const int32_t *qh = reinterpret_cast<const int32_t *>(sq);
+    const int32_t *eh = reinterpret_cast<const int32_t *>(se);
+    v.n1 = qh[0];
+    v.n2 = eh[0];
+    anneal_entry<W1, W2, LORDER, false>(p, v, team, tl, red, (uint32_t)eh[1], (uint32_t)qh[1], xw, qi, first + team);
+  } else {
+    // validation: this CTA is reference block b; one team of 128 threads; entries b, b+128, ... in pool order
+    const int b = p.xw_blocks[blockIdx.x];
+    uint32_t *st = p.xw_states + ((size_t)b * SATS_REF_GRID_THREADS + tl) * 6;
+    xw.load(st);
+    uint32_t phase = 0;
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, p.qblob_bytes[qi]);
+      tma_load_1d(sq, p.qblobs + p.qblob_off[qi], p.qblob_bytes[qi], bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    const int32_t *qh = reinterpret_cast<const int32_t *>(sq);
+    v.n1 = qh[0];
+    for (int pos = b; pos < p.pool_count; pos += SATS_REF_GRID_BLOCKS) {
+      const int e = p.pool_list[pos];
+      if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, p.blob_bytes[e]);
+        tma_load_1d(se, p.blobs + p.blob_off[e], p.blob_bytes[e], bar);
+      }
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+      const int32_t *eh = reinterpret_cast<const int32_t *>(se);
+      v.n2 = eh[0];
+      anneal_entry<W1, W2, LORDER, true>(p, v, 0, tl, red, (uint32_t)eh[1], (uint32_t)qh[1], xw, qi, e);
+    }
+    xw.store(st);
+  }
+}
+
+#endif  // SATS_KERNEL_CUH
