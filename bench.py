@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SA tableau-search hot path (BASELINE.json metric).
+
+Workload (BASELINE.json configs[4], the configuration the metric is quoted on): query D2PHLB1 (n1 = 19, LTYPE=T
+LORDER=T LSOLN=F) against a synthetic 100 000-structure database (bootstrap of the reference's 586 real structures,
+seed 20240502, size-sorted), 128 restarts x 100 moves, production (Philox) streams.  One "step" = one query searched
+against the whole database.  With N GPUs the fixed database is split into N cost-weighted shards, one process per
+GPU, no data-path collective ("strong" scaling); value = all structures searched / max-over-ranks device time.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm
+  python bench.py --impl reference [...]                      the reference's own `-c` CPU path, all host cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+DB_SIZE = 100_000
+DB_SEED = 20240502
+QUERY = "D2PHLB1"
+RESTARTS = 128
+MOVES = 100
+# reference-width algorithmic on-chip bytes per move-eval for D2PHLB1 (n1=19, LORDER=T)
+ALGO_BYTES_PER_MOVE = 148.0
+SM_COUNT = 148
+SMEM_BYTES_PER_CLK_PER_SM = 128
+ISSUE_SLOTS_PER_CLK_PER_SM = 4
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text()), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_db(S):
+    base = S.Database.read_packed(ROOT / "tests" / "golden" / "small586.satsdb")
+    return base.bootstrap(DB_SIZE, DB_SEED, True)
+
+
+def query_db(S):
+    qs = S.Database.read_packed(ROOT / "tests" / "golden" / "queries.satsdb")
+    return qs.select([qs.find(QUERY)])
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+REF_BIN = ROOT / "oracle" / "_ref" / "cudaSaTabsearch_ref"
+
+
+def stratified_sample(S, db, count):
+    idx = np.linspace(0, len(db) - 1, count).round().astype(np.int32)
+    return db.select(idx)
+
+
+def run_reference_cpu(S, db, per_proc: int, procs: int):
+    """P independent `cudaSaTabsearch -c` processes on P shards of a size-stratified sample (the reference is single
+    threaded with a process-global drand48 stream: BASELINE.md section 3).  Returns (structures/s, detail)."""
+    sample = stratified_sample(S, db, per_proc * procs)
+    qs = query_db(S)
+    with tempfile.TemporaryDirectory() as td:
+        ps = []
+        qs.write_ascii(os.path.join(td, "q.ascii"))
+        qtext = Path(td, "q.ascii").read_text()
+        for p in range(procs):
+            shard = sample.select(np.arange(p, per_proc * procs, procs, dtype=np.int32))
+            shard.write_ascii(os.path.join(td, "db%d.ascii" % p))
+            Path(td, "in%d" % p).write_text("db%d.ascii\nT T F\n%s" % (p, qtext))
+        t0 = time.perf_counter()
+        for p in range(procs):
+            ps.append(subprocess.Popen([str(REF_BIN), "-c", "-r", str(RESTARTS)], stdin=open(os.path.join(td, "in%d" % p)),
+                                       stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, cwd=td, text=True))
+        search_ms = []
+        for pr in ps:
+            err = pr.communicate()[1]
+            if pr.returncode != 0:
+                raise RuntimeError("reference binary failed: " + err[-500:])
+            search_ms.append(sum(float(x) for x in re.findall(r"host execution time ([0-9.]+) ms", err)))
+        wall = time.perf_counter() - t0
+    slowest = max(search_ms) / 1e3            # the reference's own timer around sa_tabsearch_host (search only)
+    return per_proc * procs / slowest, {"wall_s": wall, "slowest_search_s": slowest}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import cuda_satabsearch_b200 as S
+    if not REF_BIN.exists():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/cudaSaTabsearch_ref not built"}))
+        return
+    db = synthetic_db(S)
+    cores = host_cores()
+    per_proc = 600                       # ~1.7 s of single-core work per process per step
+    vals = []
+    for it in range(args.warmup + args.steps):
+        v, _ = run_reference_cpu(S, db, per_proc, cores)
+        if it >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    sample = ("%d processes x %d structures (size-stratified sample of the 100k synthetic db), reference -c path, "
+              "rate = structures / slowest process's own 'host execution time'" % (cores, per_proc))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "structures/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * per_proc * cores / value,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic",
+        "config": CONFIG, "move_evals_per_s": value * RESTARTS * MOVES,
+        "cpu_baseline": {"value": value, "unit": "structures/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "structures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+METRIC = "db structures searched/sec at 128 restarts (SA move-evals/sec = value x 128 x 100)"
+CONFIG = {"workload": "D2PHLB1 (n1=19, T T F) vs synthetic 100k-structure db (bootstrap of 586 real structures, seed "
+                      "20240502, size-sorted), 128 restarts x 100 moves, Philox streams; db sharded over the GPUs "
+                      "(cost-weighted LPT partition)",
+          "db_structures": DB_SIZE, "restarts": RESTARTS, "queries_per_step": 1,
+          "l2": "L2 flushed between timed steps (256 MiB write)"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def ours(args):
+    import torch
+    import cuda_satabsearch_b200 as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_gpus = max(world, 1)
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("launch N>1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    db = synthetic_db(S)
+    qs = query_db(S)
+    sr = S.Searcher(db, local, rank, n_gpus)
+    n_local = sr.entries
+    p = S.default_params(lorder=1, lsoln=0, restarts=RESTARTS, rng_mode=S.RNG_PHILOX, seed=1234)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    scores = np.zeros((1, len(db)), np.int32)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sr.upload(qs)
+    for _ in range(max(args.warmup, 3)):
+        sr.launch(p, 0, timed=True)
+    # ---- device-timed kernel-only steps (inputs resident in HBM)
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    l0 = sr.launches
+    dev_ms = 0.0
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        dev_ms += sr.launch(p, 0, timed=True)
+    barrier()
+    wall_ms = (time.perf_counter() - wall0) * 1e3
+    launches = sr.launches - l0
+    # ---- end to end through the public call, host buffers in, host buffers out
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        sr.search(qs, p, scores=scores)
+    barrier()
+    e2e_ms = (time.perf_counter() - e0) * 1e3
+    clk = clocks.stop() if rank == 0 else None
+
+    if dist is not None:
+        t = torch.tensor([dev_ms, e2e_ms, float(launches), wall_ms], device=dev, dtype=torch.float64)
+        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_ms, wall_ms = float(mx[0]), float(mx[1]), float(mx[3])
+        launches = int(sm[2])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_kind = load_peaks()
+    ms_per_step = dev_ms / args.steps
+    value = DB_SIZE / (ms_per_step / 1e3)
+    moves = value * RESTARTS * MOVES
+    e2e_value = DB_SIZE / (e2e_ms / args.steps / 1e3)
+    sm_mhz = peaks.get("sm_max_mhz", 1965.0)
+    smem_peak = n_gpus * SM_COUNT * SMEM_BYTES_PER_CLK_PER_SM * sm_mhz * 1e6 / 1e9      # GB/s at max clock
+    achieved = moves * ALGO_BYTES_PER_MOVE / 1e9
+    prof = {}
+    pj = ROOT / "profiles" / "latest.json"
+    if pj.exists():
+        prof = json.loads(pj.read_text())
+    blob_bytes = prof.get("algorithmic_hbm_bytes_per_step")
+    roofline = {
+        "bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
+        "traffic": prof.get("dram_bytes_per_step"),
+        "note": "north star: the bound is shared-memory bandwidth / SM issue slots, not HBM or tensor cores. achieved = "
+                "move-evals/s x 148 B (SURVEY 8d reference-width on-chip bytes per move, n1=19 LORDER=T); peak = N x 148 SMs x "
+                "128 B/clk x %.0f MHz (max SM clock, %s)" % (sm_mhz, peak_kind),
+        "issue": {"warp_inst_per_move": prof.get("warp_inst_per_move"),
+                  "achieved_frac_of_issue_slots": (moves * prof["warp_inst_per_move"] /
+                                                   (n_gpus * SM_COUNT * ISSUE_SLOTS_PER_CLK_PER_SM * sm_mhz * 1e6))
+                  if prof.get("warp_inst_per_move") else None},
+        "hbm": {"algorithmic_gbs": (blob_bytes / (ms_per_step / 1e3) / 1e9) if blob_bytes else None,
+                "peak_gbs": peaks.get("hbm_gbs"), "peak_kind": peak_kind},
+    }
+    cpu = None
+    if n_gpus == 1 and REF_BIN.exists() and not args.no_cpu:
+        v, det = run_reference_cpu(S, db, 4000, 1)
+        cpu = {"value": v, "unit": "structures/s", "cores": 1, "kind": "reference",
+               "sample": "4000 structures (size-stratified sample of the 100k synthetic db), reference -c path, one "
+                         "process; rate = structures / its own 'host execution time' (%.1f s)" % det["slowest_search_s"]}
+    line = {
+        "metric": METRIC, "value": value, "unit": "structures/s", "n_gpus": n_gpus, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic", "config": CONFIG,
+        "move_evals_per_s": moves, "wall_ms_per_step_incl_l2_flush": wall_ms / args.steps,
+        "e2e": {"value": e2e_value, "unit": "structures/s", "h2d_bytes_per_step": int(n_gpus * (128 + 8 * 19 * 19 + 12)),
+                "d2h_bytes_per_step": int(4 * DB_SIZE), "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+        "local_entries_rank0": n_local,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,159 @@
+"""CPU-side tests of libsats.so: the library loads, exports every symbol include/sats.h declares, and its host
+logic (parser, packed cache, ASCII writer, statistics, result formatter, partitioner, stdin grammars) behaves like
+the reference's host code.  No search is run here (that needs a GPU and must fail loudly without one)."""
+import hashlib
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import cuda_satabsearch_b200 as S
+from _refio import GOLDEN, REPO, format_entry, read_packed, stats
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = (REPO / "include" / "sats.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(sats_[a-z0-9_]+)\s*\(", hdr))
+    names |= set(re.findall(r"extern const double (sats_[a-z_]+);", hdr))
+    assert len(names) >= 35
+    out = subprocess.run(["nm", "-D", "--defined-only", str(S.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\b[TDRB] (sats_[a-z0-9_]+)", out))
+    assert names - exported == set(), names - exported
+    S.lib()          # binds every function; AttributeError if one is missing
+
+
+def test_no_cpu_fallback_without_gpu():
+    if S.device_count() > 0:
+        pytest.skip("GPU present")
+    db = S.Database.read_packed(GOLDEN / "test1.satsdb")
+    with pytest.raises(S.SatsError, match="no CUDA device"):
+        S.Searcher(db)
+
+
+def test_product_never_touches_the_oracle():
+    for p in list((REPO / "cuda_satabsearch_b200").rglob("*")) + [REPO / "include" / "sats.h"]:
+        if p.is_file() and p.suffix in (".py", ".c", ".cpp", ".cu", ".cuh", ".h") or p.name == "Makefile":
+            txt = p.read_text(errors="ignore")
+            assert "sats_oracle" not in txt and "oracle/" not in txt.replace("the oracle", ""), p
+
+
+@pytest.mark.parametrize("key", ["small586", "test1", "test2", "d1qlpa", "d2pq6a1", "queries"])
+def test_packed_reader_matches_independent_reader(key):
+    db = S.Database.read_packed(GOLDEN / (key + ".satsdb"))
+    ref = read_packed(GOLDEN / (key + ".satsdb"))
+    assert len(db) == len(ref)
+    step = max(1, len(ref) // 60)
+    for i in list(range(0, len(ref), step)) + [len(ref) - 1]:
+        t, d = db.get(i)
+        assert db.name(i) == ref[i].name and db.order(i) == ref[i].n
+        assert np.array_equal(t, ref[i].tab) and np.array_equal(d, ref[i].dmat)
+
+
+def test_ascii_writer_is_byte_identical_to_reference_files(tmp_path, golden):
+    for key, meta in golden["ascii_md5"].items():
+        db = S.Database.read_packed(GOLDEN / (key + ".satsdb"))
+        out = tmp_path / (key + ".ascii")
+        db.write_ascii(out)
+        raw = out.read_bytes()
+        if len(raw) + 1 == meta["bytes"]:
+            raw += b"\n"
+        assert hashlib.md5(raw).hexdigest() == meta["md5"], key
+
+
+def test_ascii_parse_roundtrip_and_packed_roundtrip(tmp_path):
+    ref = read_packed(GOLDEN / "small586.satsdb")
+    text = "\n".join(format_entry(s) for s in ref)
+    db = S.Database.parse_ascii(text)
+    assert len(db) == 586
+    for i in (0, 1, 17, 300, 585):
+        t, d = db.get(i)
+        assert np.array_equal(t, ref[i].tab) and np.array_equal(d, ref[i].dmat) and db.name(i) == ref[i].name
+    db.write_packed(tmp_path / "x.satsdb")
+    assert (tmp_path / "x.satsdb").read_bytes() == (GOLDEN / "small586.satsdb").read_bytes()
+
+
+def test_parser_edge_cases():
+    assert len(S.Database.parse_ascii("")) == 0                       # empty db
+    one = "A          1\ne  \n 0.000 \n"
+    db = S.Database.parse_ascii(one)
+    assert len(db) == 1 and db.order(0) == 1 and db.get(0)[0][0, 0] == 0
+    with pytest.raises(S.SatsError, match="invalid tableaux code"):
+        S.Database.parse_ascii("B          2\ne  \nXX e  \n 0.000 \n 1.000  0.000 \n")
+    with pytest.raises(S.SatsError, match="Bad helix type"):
+        S.Database.parse_ascii("B          1\nxz \n 0.000 \n")
+    with pytest.raises(S.SatsError, match="truncated"):
+        S.Database.parse_ascii("B          2\ne  \nPE e  \n 0.000 \n")
+    # structures larger than MAXDIM are skipped with a warning, the rest is kept (parsetableaux.c:457-465)
+    n = 112
+    big = "BIG      %4d\n" % n + "".join("PE " * i + "e  \n" for i in range(n)) + "".join(" 1.000 " * (i + 1) + "\n" for i in range(n))
+    db = S.Database.parse_ascii(big + "\n" + one)
+    assert len(db) == 1 and db.name(0) == "A"
+    # the 5x5 code alphabet incl. '?' (parsetableaux.c:92-138)
+    q = "C          2\nxg \n?? xi \n 3.000 \n 9.999  2.000 \n"
+    t, d = S.Database.parse_ascii(q).get(0)
+    assert t.tolist() == [[3, 0x44], [0x44, 2]] and d[1, 0] == np.float32(9.999)
+
+
+def test_input_and_idlist_grammar():
+    ref = read_packed(GOLDEN / "queries.satsdb")
+    body = "\n".join(format_entry(s) for s in ref[:3])
+    dbf, lt, lo, ls, qs = S.parse_input("some/db.ascii\nT F T\n" + body)
+    assert (dbf, lt, lo, ls) == ("some/db.ascii", True, False, True)
+    assert qs.names() == [s.name for s in ref[:3]]
+    with pytest.raises(S.SatsError, match="no query structures"):
+        S.parse_input("db\nT T F\n")
+    # ids are cut to 7 characters like cudaSaTabsearch.cu:657
+    assert S.parse_idlist("d1ubia_\nd2phlb1xyz\n\nabc\n") == ["d1ubia_", "d2phlb1", "abc"]
+    db = S.Database.read_packed(GOLDEN / "small586.satsdb")
+    assert db.find("D1KCUL1") == 0                                    # strcasecmp, cudaSaTabsearch.cu:747
+    with pytest.raises(S.SatsError, match="not found"):
+        db.find("nosuch")
+
+
+def test_statistics_and_formatter_reproduce_reference_stdout(golden, oracle):
+    """Scores from the golden reference run -> sats_format_block must re-create the reference's stdout."""
+    for cid in ("d1ubia_small_r128", "d2phlb1_small_r128", "sheetbc_small_TFT_r128", "d1ubia_test1_default"):
+        case = golden["cases"][cid]
+        db = S.Database.read_packed(GOLDEN / (case["db"] + ".satsdb"))
+        blk = case["blocks"][0]
+        qs = S.Database.read_packed(GOLDEN / "queries.satsdb")
+        qn = qs.order(qs.find(blk["query"]))
+        scores = np.array(blk["scores"], np.int32)
+        maps = None
+        if case["lsoln"]:
+            maps = np.full((len(db), S.MAP_STRIDE), -1, np.int32)
+            for e, pairs in enumerate(blk["maps"]):
+                for k, j in pairs:
+                    maps[e, k - 1] = j - 1
+        text = db.format_block(blk["query"], qn, case["dbfile"], case["lorder"], case["lsoln"], scores, maps)
+        assert hashlib.md5(text.encode()).hexdigest() == case["stdout_md5"], cid
+    for score, n1, n2 in [(54, 8, 8), (-3, 19, 40), (0, 9, 1), (7, 101, 67)]:
+        n2s, z, p = stats(score, n1, n2)
+        assert S.norm2(score, n1, n2) == n2s and S.z_gumbel(int(n2s)) == z and S.pv_gumbel(z) == p
+
+
+def test_partition_is_balanced_and_complete():
+    db = S.Database.read_packed(GOLDEN / "small586.satsdb")
+    orders = db.orders()
+    for n in (1, 2, 3, 8):
+        own = db.partition(n)
+        assert own.min() == 0 and own.max() == n - 1
+        cost = 10.0 + 0.25 * np.minimum(orders, 40)
+        loads = np.array([cost[own == r].sum() for r in range(n)])
+        assert loads.max() - loads.min() <= cost.max() + 1e-9          # LPT bound
+    big = db.bootstrap(20000, 20240501, True)
+    o = big.orders()
+    assert len(big) == 20000 and np.all(np.diff(o) >= 0) and big.name(0).startswith("s")
+    assert abs(o.mean() - orders.mean()) < 0.5
+    again = db.bootstrap(20000, 20240501, True)
+    assert np.array_equal(again.orders(), o)                            # deterministic
+
+
+def test_select_and_from_structures_roundtrip():
+    ref = read_packed(GOLDEN / "small586.satsdb")[:20]
+    db = S.Database.from_structures([s.name for s in ref], [s.tab for s in ref], [s.dmat for s in ref])
+    sub = db.select([5, 0, 19])
+    assert sub.names() == [ref[5].name, ref[0].name, ref[19].name]
+    assert np.array_equal(sub.get(2)[1], ref[19].dmat)
