@@ -47,13 +47,13 @@ def raw(rep):
             print("%-78s %-16s %s" % (w, u[idx[w]], " | ".join(r[idx[w]][:26] for r in rows[2:])))
 
 
-def source(rep, kid, src_path="cuda_satabsearch_b200/csrc/sats_kernel.cuh", top=60):
+def source(rep, kid, top=60):
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-id", ":::" + kid],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     h = [i for i, r in enumerate(rows) if r and r[0] == "Line No"][0]
     fn = [r[1] for r in rows[:h] if r and r[0] == "Function Name"]
-    src = open(src_path).read().split("\n")
+    src = {}
     agg = collections.defaultdict(lambda: [0, 0, 0])
     tot = [0, 0, 0]
     for r in rows[h + 1:]:
@@ -63,6 +63,7 @@ def source(rep, kid, src_path="cuda_satabsearch_b200/csrc/sats_kernel.cuh", top=
             v = (int(r[7]), int(r[8]), int(r[6]))
         except ValueError:
             continue
+        src[int(r[0])] = r[1]
         for k in range(3):
             agg[int(r[0])][k] += v[k]
             tot[k] += v[k]
@@ -70,7 +71,7 @@ def source(rep, kid, src_path="cuda_satabsearch_b200/csrc/sats_kernel.cuh", top=
     print("# warp instructions executed: %d ; thread instructions: %d ; avg active threads/instruction: %.2f" % (tot[0], tot[1], tot[1] / max(tot[0], 1)))
     print("# line  share-of-warp-inst  active-threads/inst  share-of-stall-samples  source")
     for ln, (ie, te, sm) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
-        print("%4d  %5.1f%%  %4.1f  %5.1f%%  %s" % (ln, 100 * ie / tot[0], te / max(ie, 1), 100 * sm / max(tot[2], 1), src[ln - 1].strip()[:120]))
+        print("%4d  %5.1f%%  %4.1f  %5.1f%%  %s" % (ln, 100 * ie / tot[0], te / max(ie, 1), 100 * sm / max(tot[2], 1), src.get(ln, "").strip()[:120]))
 
 
 if __name__ == "__main__":
