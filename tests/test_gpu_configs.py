@@ -1,0 +1,150 @@
+"""BASELINE.json configurations at (or near) their full sizes: oracle comparison where the oracle finishes in seconds,
+size-independent properties at full size, and the statistical agreement of production mode with the reference."""
+import numpy as np
+import pytest
+
+import cuda_satabsearch_b200 as S
+from _refio import GOLDEN, Structure
+
+pytestmark = pytest.mark.gpu
+
+
+def structures_of(db, idx):
+    out = []
+    for i in idx:
+        t, d = db.get(int(i))
+        out.append(Structure(db.name(int(i)), t, d))
+    return out
+
+
+def as_db(structs):
+    return S.Database.from_structures([s.name for s in structs], [s.tab for s in structs], [s.dmat for s in structs])
+
+
+@pytest.fixture(scope="module")
+def base():
+    return S.Database.read_packed(GOLDEN / "small586.satsdb")
+
+
+def test_config2_astral_scale_validation_mode(base, fixtures, oracle):
+    """configs[1]: d1ubia_ vs synthetic ASTRAL-scale db (14 297 structures, size-sorted), validation-RNG mode:
+    (score, map) of every entry must equal the oracle's reference-grid run."""
+    db = base.bootstrap(14297, 20240501, True)
+    q = fixtures["queries_by_name"]["D1UBIA_"]
+    sr = S.Searcher(db, 0)
+    p = S.default_params(lorder=1, lsoln=1, restarts=128, rng_mode=S.RNG_XORWOW_GRID, seed=1234)
+    sc, mp = sr.search(as_db([q]), p)
+    ents = structures_of(db, range(len(db)))
+    ws, wm = oracle.search_xorwow_grid(q, ents, oracle.xorwow_states(), lorder=True, lsoln=True, restarts=128)
+    assert np.array_equal(sc[0], ws)
+    assert np.array_equal(mp[0, :, :q.n], wm[:, :q.n])
+    sr.close()
+
+
+def test_config3_query_list_200_queries(base, fixtures, oracle):
+    """configs[2]: 200 queries drawn from the synthetic 15k db (seed 200) searched in ONE batched call; a random
+    sample of (query, entry) pairs is checked against the oracle, every score against its upper bound."""
+    db = base.bootstrap(14297, 20240501, True)
+    rng = np.random.default_rng(200)
+    qidx = rng.choice(len(db), 200, replace=False).astype(np.int32)
+    queries = db.select(qidx)
+    sr = S.Searcher(db, 0)
+    p = S.default_params(lorder=1, lsoln=0, restarts=128, seed=4242)
+    sc, _ = sr.search(queries, p, query_index_base=0)
+    assert sc.shape == (200, len(db)) and sc.min() > np.iinfo(np.int32).min
+    orders = db.orders().astype(np.int64)
+    for k in range(200):
+        n1 = int(orders[qidx[k]])
+        mn = np.minimum(n1, orders)
+        assert np.all(sc[k] <= mn * (mn - 1))                      # <= 2 * C(min(n1, n2), 2)
+    for k in (0, 57, 199):
+        pick = np.sort(rng.choice(len(db), 250, replace=False)).astype(np.int32)
+        q = structures_of(db, [qidx[k]])[0]
+        ws, _ = oracle.search_philox(q, structures_of(db, pick), entry_ids=pick, lorder=True, lsoln=False, restarts=128,
+                                     seed=4242, query_index=k)
+        assert np.array_equal(sc[k, pick], ws)
+    sr.close()
+
+
+def test_config4_sheet_query_unordered_maps_1024_restarts(base, fixtures, oracle):
+    """configs[3]: SHEETBC (n1 = 9), LORDER=F LSOLN=T, 1024 restarts, synthetic db: scores and SSE maps."""
+    db = base.bootstrap(3000, 20240503, True)
+    q = fixtures["queries_by_name"]["SHEETBC"]
+    sr = S.Searcher(db, 0)
+    p = S.default_params(lorder=0, lsoln=1, restarts=1024, seed=9)
+    sc, mp = sr.search(as_db([q]), p)
+    pick = np.arange(0, 3000, 10, dtype=np.int32)
+    ws, wm = oracle.search_philox(q, structures_of(db, pick), entry_ids=pick, lorder=False, lsoln=True, restarts=1024, seed=9)
+    assert np.array_equal(sc[0, pick], ws)
+    assert np.array_equal(mp[0, pick, :q.n], wm[:, :q.n])
+    # every reported map must be a valid one-to-one, type-respecting matching whose full score is the reported score
+    ents = structures_of(db, pick)
+    for e, s in zip(pick, ents):
+        m = mp[0, e, :q.n]
+        used = m[m >= 0]
+        assert len(set(used.tolist())) == len(used) and (used < s.n).all()
+        assert all(q.tab[i, i] == s.tab[j, j] for i, j in enumerate(m) if j >= 0)
+        assert oracle.full_score(q, s, m) == sc[0, e]
+    sr.close()
+
+
+def test_config5_full_size_properties(base, fixtures):
+    """configs[4] at full size (100 000 structures, D2PHLB1, 128 restarts): deterministic, invariant under
+    sharding (2 shards merged == unsharded), bounded."""
+    db = base.bootstrap(100000, 20240502, True)
+    q = as_db([fixtures["queries_by_name"]["D2PHLB1"]])
+    p = S.default_params(lorder=1, lsoln=0, restarts=128, seed=1234)
+    sr = S.Searcher(db, 0)
+    a, _ = sr.search(q, p)
+    b, _ = sr.search(q, p)
+    assert np.array_equal(a, b)
+    sr.close()
+    merged = np.full_like(a, np.iinfo(np.int32).min)
+    for r in range(2):
+        sh = S.Searcher(db, 0, r, 2)
+        sh.search(q, p, scores=merged)
+        sh.close()
+    assert np.array_equal(merged, a)
+    orders = db.orders().astype(np.int64)
+    mn = np.minimum(19, orders)
+    assert np.all(a[0] <= mn * (mn - 1))
+
+
+def test_production_mode_agrees_statistically_with_reference(base, fixtures, golden, oracle):
+    """North star, part 2: Philox streams differ from drand48, so per-entry scores differ run to run, but the ranking
+    quality must be the same.  Truth = the reference's own converged run (its captured 2013 job, 4096 restarts).
+    Eight production runs (different seeds) are compared with eight reference-path runs (oracle in drand48 mode, the
+    first being the golden reference output itself): mean top-50 overlap and mean ROC AUC must agree within the
+    run-to-run spread."""
+    blocks = golden["captured"]["cpu_2013_d2phlb1_r4096"]["blocks"]
+    ents = fixtures["small586"]
+    conv = {n: s for b in blocks for n, s in zip(b["names"], b["scores"])}
+    truth = np.array([conv[s.name] for s in ents])
+    q = fixtures["queries_by_name"]["D2PHLB1"]
+
+    def top(x, k=50):
+        return set(np.argsort(-x, kind="stable")[:k].tolist())
+
+    def auc(score, positives):
+        pos, neg = score[positives], score[~positives]
+        return ((pos[:, None] > neg[None, :]).sum() + 0.5 * (pos[:, None] == neg[None, :]).sum()) / (len(pos) * len(neg))
+
+    positives = np.zeros(len(truth), bool)
+    positives[list(top(truth, 25))] = True
+    seeds = [1234, 1, 2, 3, 4, 5, 6, 7]
+    ref_runs = []
+    for sd in seeds:
+        oracle.srand48(sd)
+        ref_runs.append(oracle.search_drand48(q, ents, True, False, 128)[0])
+    assert ref_runs[0].tolist() == golden["cases"]["d2phlb1_small_r128"]["blocks"][0]["scores"]
+    sr = S.Searcher(base, 0)
+    our_runs = [sr.search(as_db([q]), S.default_params(restarts=128, seed=sd))[0][0] for sd in seeds]
+    sr.close()
+    ref_auc = np.array([auc(x, positives) for x in ref_runs]); our_auc = np.array([auc(x, positives) for x in our_runs])
+    ref_ov = np.array([len(top(x) & top(truth)) for x in ref_runs]); our_ov = np.array([len(top(x) & top(truth)) for x in our_runs])
+    spread = max(ref_auc.std(), our_auc.std(), 0.004)
+    assert abs(our_auc.mean() - ref_auc.mean()) < 3 * spread / np.sqrt(len(seeds)) + 0.003, (our_auc, ref_auc)
+    assert abs(our_ov.mean() - ref_ov.mean()) < 3.0 and our_ov.min() >= 30, (our_ov, ref_ov)
+    ref_mean = np.mean([x.mean() for x in ref_runs]); our_mean = np.mean([x.mean() for x in our_runs])
+    assert abs(our_mean - ref_mean) < 0.1, (our_mean, ref_mean)
+    assert np.corrcoef(np.mean(our_runs, 0), np.mean(ref_runs, 0))[0, 1] > 0.985
