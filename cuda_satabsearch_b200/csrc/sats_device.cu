@@ -43,6 +43,12 @@ struct sats_searcher {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // bucket launches of one search go round-robin over side streams so that the tail of one size bucket
+  // overlaps the head of the next (forked from / joined to `stream` with events)
+  static const int kSide = 4;
+  cudaStream_t side[kSide] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t side_done[kSide] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr;
   int db_count = 0;                       // entries of the whole database (output indexing)
   std::vector<int32_t> sorted_orig;       // local sorted position -> original db index (decreasing order)
   std::vector<int32_t> sorted_order;
@@ -166,6 +172,11 @@ extern "C" int sats_searcher_create(const sats_db *db, int device, int shard_ran
   CKF(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   CKF(cudaEventCreate(&s->ev0));
   CKF(cudaEventCreate(&s->ev1));
+  CKF(cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming));
+  for (int i = 0; i < sats_searcher::kSide; i++) {
+    CKF(cudaStreamCreateWithFlags(&s->side[i], cudaStreamNonBlocking));
+    CKF(cudaEventCreateWithFlags(&s->side_done[i], cudaEventDisableTiming));
+  }
   CKF(cudaMalloc(&s->d_blobs, blobs.size()));
   CKF(cudaMalloc(&s->d_blob_off, std::max<size_t>(1, local.size()) * 8));
   CKF(cudaMalloc(&s->d_blob_bytes, std::max<size_t>(1, local.size()) * 4));
@@ -204,6 +215,11 @@ extern "C" void sats_searcher_free(sats_searcher *s)
   cudaFreeHost(s->h_qstage); cudaFreeHost(s->h_scores); cudaFreeHost(s->h_maps);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->fork) cudaEventDestroy(s->fork);
+  for (int i = 0; i < sats_searcher::kSide; i++) {
+    if (s->side_done[i]) cudaEventDestroy(s->side_done[i]);
+    if (s->side[i]) cudaStreamDestroy(s->side[i]);
+  }
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -416,6 +432,9 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
     } else {
       const int tw = std::min(128, ((pp->restarts + 31) / 32) * 32);
       k.tw = tw;
+      CK(cudaEventRecord(s->fork, s->stream));
+      for (int i = 0; i < sats_searcher::kSide; i++) CK(cudaStreamWaitEvent(s->side[i], s->fork, 0));
+      int nlaunch = 0;
       // runs of consecutive queries with the same mask width share launches (grid.y)
       for (int q0 = 0; q0 < Q;) {
         int q1 = q0 + 1;
@@ -452,12 +471,17 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
           k.item_first = b0; k.item_count = b1 - b0;
           size_t smem = 16 + k.sm_query_bytes + (size_t)k.teams * k.sm_team_bytes;
           dim3 grid((unsigned)((k.item_count + k.teams - 1) / k.teams), (unsigned)(q1 - q0));
-          fn<<<grid, k.teams * tw, smem, s->stream>>>(k);
+          fn<<<grid, k.teams * tw, smem, s->side[nlaunch % sats_searcher::kSide]>>>(k);
           CK(cudaGetLastError());
           s->launches++;
+          nlaunch++;
           b0 = b1;
         }
         q0 = q1;
+      }
+      for (int i = 0; i < sats_searcher::kSide; i++) {
+        CK(cudaEventRecord(s->side_done[i], s->side[i]));
+        CK(cudaStreamWaitEvent(s->stream, s->side_done[i], 0));
       }
     }
   }
