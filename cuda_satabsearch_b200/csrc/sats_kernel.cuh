@@ -121,8 +121,14 @@ template <int W> __device__ __forceinline__ void bit_clear(uint32_t (&m)[W], int
 #pragma unroll
   for (int w = 0; w < W; w++) if (W == 1 || (b >> 5) == w) m[w] &= ~(1u << (b & 31));
 }
-// mask of bit positions < x within one word (x may be <= 0 or >= 32)
-__device__ __forceinline__ uint32_t below(int x) { return x <= 0 ? 0u : (x >= 32 ? 0xffffffffu : ((1u << x) - 1u)); }
+// mask of bit positions < x within one word (x may be <= 0 or >= 32).  PTX shl.b32 clamps shift amounts above 31
+// (the result is 0), so ~(~0 << max(x, 0)) is exact on the whole range without branches.
+__device__ __forceinline__ uint32_t below(int x)
+{
+  uint32_t r;
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(0xffffffffu), "r"((uint32_t)max(x, 0)));
+  return ~r;
+}
 
 // highest set bit with index <= i, or -1
 template <int W> __device__ __forceinline__ int top_at_or_below(const uint32_t (&m)[W], int i)
@@ -209,9 +215,9 @@ struct Xorwow {
 // ------------------------------------------------------------------------------------------------ scoring
 __device__ __forceinline__ int zeta(uint32_t a, uint32_t b)
 {
-  uint32_t x = a ^ b;
-  int hits = ((x & 0xF0u) == 0u) + ((x & 0x0Fu) == 0u);
-  return hits ? hits : -2;
+  // nibbles hold 0..4, so (nibble xor) + 7 carries into bit 3 of that nibble exactly when the nibbles differ
+  const int miss = __popc(((a ^ b) + 0x77u) & 0x88u);      // 0, 1 or 2 differing letters
+  return miss == 2 ? -2 : 2 - miss;
 }
 __device__ __forceinline__ int gated(uint2 q, uint2 e)
 {
