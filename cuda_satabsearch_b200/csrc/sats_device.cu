@@ -458,7 +458,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
           kernel_fn fn = pick_kernel(w1, words_for(n2max), pp->lorder != 0, false);
           // teams per CTA: as many as fit while keeping the most warps resident per SM
           int best_teams = 0, best_warps = -1;
-          for (int teams = 512 / tw; teams >= 1; teams >>= 1) {
+          for (int teams = SATS_K_MAXTHREADS / tw; teams >= 1; teams--) {
             size_t smem = 16 + k.sm_query_bytes + (size_t)teams * k.sm_team_bytes;
             if (smem > (size_t)kMaxSmem) continue;
             int ctas = 0;

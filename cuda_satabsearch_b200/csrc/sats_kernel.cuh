@@ -475,8 +475,12 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
 //   [0,16)                      mbarrier
 //   [16, 16 + sm_query_bytes)   query blob
 //   then per team: entry blob (sm_entry_bytes) | byte maps (mapwords*tw*4) | best maps (same, if lsoln) | 64 B reduce scratch
+#ifndef SATS_K_MAXTHREADS
+#define SATS_K_MAXTHREADS 384
+#define SATS_K_MINBLOCKS 3
+#endif
 template <int W1, int W2, bool LORDER, bool XORWOW>
-__global__ void __launch_bounds__(512) sats_anneal_kernel(const SatsKParams p)
+__global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anneal_kernel(const SatsKParams p)
 {
   using namespace satsk;
   extern __shared__ __align__(128) uint8_t smem[];
