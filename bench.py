@@ -263,19 +263,26 @@ def ours(args):
     pj = ROOT / "profiles" / "latest.json"
     if pj.exists():
         prof = json.loads(pj.read_text())
-    blob_bytes = prof.get("algorithmic_hbm_bytes_per_step")
+    orders = db.orders().astype(np.int64)
+    blob_bytes = float(((80 + 8 * orders * orders + 15) // 16 * 16).sum())      # every entry blob is read once per query
     roofline = {
         "bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
         "traffic": prof.get("dram_bytes_per_step"),
         "note": "north star: the bound is shared-memory bandwidth / SM issue slots, not HBM or tensor cores. achieved = "
                 "move-evals/s x 148 B (SURVEY 8d reference-width on-chip bytes per move, n1=19 LORDER=T); peak = N x 148 SMs x "
-                "128 B/clk x %.0f MHz (max SM clock, %s)" % (sm_mhz, peak_kind),
+                "128 B/clk x %.0f MHz (max SM clock, %s); traffic = ncu dram bytes per step (%s)" % (
+                    sm_mhz, peak_kind, prof.get("capture", "no capture")),
         "issue": {"warp_inst_per_move": prof.get("warp_inst_per_move"),
-                  "achieved_frac_of_issue_slots": (moves * prof["warp_inst_per_move"] /
-                                                   (n_gpus * SM_COUNT * ISSUE_SLOTS_PER_CLK_PER_SM * sm_mhz * 1e6))
-                  if prof.get("warp_inst_per_move") else None},
-        "hbm": {"algorithmic_gbs": (blob_bytes / (ms_per_step / 1e3) / 1e9) if blob_bytes else None,
-                "peak_gbs": peaks.get("hbm_gbs"), "peak_kind": peak_kind},
+                  "avg_active_threads_per_inst": prof.get("avg_active_threads_per_inst"),
+                  "achieved_warp_inst_per_s": moves * prof["warp_inst_per_move"] if prof.get("warp_inst_per_move") else None,
+                  "peak_warp_inst_per_s": n_gpus * SM_COUNT * ISSUE_SLOTS_PER_CLK_PER_SM * sm_mhz * 1e6,
+                  "frac": (moves * prof["warp_inst_per_move"] / (n_gpus * SM_COUNT * ISSUE_SLOTS_PER_CLK_PER_SM * sm_mhz * 1e6))
+                  if prof.get("warp_inst_per_move") else None,
+                  "note": "warp instructions per move-eval from the committed ncu capture x live move-evals/s, over 148 SMs x 4 "
+                          "schedulers x max SM clock"},
+        "hbm": {"algorithmic_bytes_per_step": blob_bytes, "algorithmic_gbs": blob_bytes / (ms_per_step / 1e3) / 1e9,
+                "peak_gbs": peaks.get("hbm_gbs"), "peak_kind": peak_kind,
+                "frac": blob_bytes / (ms_per_step / 1e3) / 1e9 / (n_gpus * peaks.get("hbm_gbs", 6650.0))},
     }
     cpu = None
     if n_gpus == 1 and REF_BIN.exists() and not args.no_cpu:
