@@ -439,7 +439,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
       for (int q0 = 0; q0 < Q;) {
         int q1 = q0 + 1;
         const int w1 = words_for(s->q_n1[q0]);
-        while (q1 < Q && words_for(s->q_n1[q1]) == w1) q1++;
+        while (q1 < Q && words_for(s->q_n1[q1]) == w1 && q1 - q0 < 65535) q1++;   // gridDim.y limit
         int n1max = 0; uint32_t qbmax = 0;
         for (int q = q0; q < q1; q++) { n1max = std::max(n1max, s->q_n1[q]); qbmax = std::max(qbmax, s->q_bytes[q]); }
         k.q_first = q0;
