@@ -300,24 +300,26 @@ struct Chain {
     return total;
   }
 
-  // deltasd (kernel.cu:502-535) over mapped SSEs only
+  // deltasd (kernel.cu:502-535) over mapped SSEs only.  Branch-free body: a missing `from` / `to` side reads row 0 and is
+  // masked out, so lanes with one-sided and two-sided moves run the same instructions.
   __device__ __forceinline__ int delta(const TeamView &v, int i, int from, int to) const
   {
     int d = 0;
+    const int fmask = from >= 0 ? -1 : 0, tmask = to >= 0 ? -1 : 0;
     const uint2 *qrow = v.qcell + i * v.n1;
-    const uint2 *frow = v.ecell + (from < 0 ? 0 : from) * v.n2;
-    const uint2 *trow = v.ecell + (to < 0 ? 0 : to) * v.n2;
+    const uint2 *frow = v.ecell + (from & fmask) * v.n2;
+    const uint2 *trow = v.ecell + (to & tmask) * v.n2;
 #pragma unroll
     for (int w = 0; w < W1; w++) {
       uint32_t b = mq[w];
       if (W1 == 1 || (i >> 5) == w) b &= ~(1u << (i & 31));
       while (b) {
-        int k = 32 * w + __ffs(b) - 1;
+        const int k = 32 * w + __ffs(b) - 1;
         b &= b - 1u;
-        int l = map_get(v.smap, k, v.tw);
-        uint2 q = qrow[k];
-        if (from >= 0) d -= gated(q, frow[l]);
-        if (to >= 0) d += gated(q, trow[l]);
+        const int l = map_get(v.smap, k, v.tw);
+        const uint2 q = qrow[k];
+        const uint2 ef = frow[l], et = trow[l];
+        d += (gated(q, et) & tmask) - (gated(q, ef) & fmask);
       }
     }
     return d;
