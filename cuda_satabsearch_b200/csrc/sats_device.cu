@@ -108,7 +108,10 @@ static void fill_cells(const sats_db *db, int e, uint8_t *cells)
   for (int i = 0; i < n; i++)
     for (int j = 0; j < n; j++) {
       float d = db->dist(e, i, j);
-      uint32_t code = db->code(e, i, j);
+      // one-hot letters (zeta() in sats_kernel.cuh counts equal letters with AND + POPC); the diagonal holds the SSE
+      // type and is never scored
+      const uint32_t raw = db->code(e, i, j);
+      uint32_t code = (1u << std::min(raw >> 4, 4u)) | (256u << std::min(raw & 15u, 4u));
       memcpy(cells + 8 * ((size_t)i * n + j), &d, 4);
       memcpy(cells + 8 * ((size_t)i * n + j) + 4, &code, 4);
     }

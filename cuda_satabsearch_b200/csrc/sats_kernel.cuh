@@ -213,11 +213,18 @@ struct Xorwow {
 };
 
 // ------------------------------------------------------------------------------------------------ scoring
+// Tableau codes are stored one-hot in the device cells (first letter -> bit 0..4, second letter -> bit 8..12, see
+// sats_device.cu:fill_cells), so the number of equal letters is one AND + POPC.
 __device__ __forceinline__ int zeta(uint32_t a, uint32_t b)
 {
-  // nibbles hold 0..4, so (nibble xor) + 7 carries into bit 3 of that nibble exactly when the nibbles differ
-  const int miss = __popc(((a ^ b) + 0x77u) & 0x88u);      // 0, 1 or 2 differing letters
-  return miss == 2 ? -2 : 2 - miss;
+  const int hits = __popc(a & b);
+  return hits ? hits : -2;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr)
+{
+  uint2 v;
+  asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ int gated(uint2 q, uint2 e)
 {
@@ -236,8 +243,19 @@ struct TeamView {
   int n1, n2, tw, mapwords;
 };
 
-__device__ __forceinline__ uint8_t map_get(const uint8_t *m, int k, int tw) { return m[(((k >> 2) * tw) << 2) + (k & 3)]; }
-__device__ __forceinline__ void map_put(uint8_t *m, int k, int tw, uint8_t v) { m[(((k >> 2) * tw) << 2) + (k & 3)] = v; }
+// byte k of a lane-private map: word k/4 of this lane is tw words after word k/4 - 1; the lane's slot is 4-byte aligned,
+// so the byte-in-word can be OR-ed into the base (one LOP3) and the word stride applied with one IMAD
+__device__ __forceinline__ uint32_t map_addr(uint32_t base, int k, int tw) { return (uint32_t)(k >> 2) * (uint32_t)(tw << 2) + (base | (uint32_t)(k & 3)); }
+__device__ __forceinline__ uint8_t map_get(const uint8_t *m, int k, int tw)
+{
+  uint32_t v;
+  asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(map_addr(smem_u32(m), k, tw)) : "memory");
+  return (uint8_t)v;
+}
+__device__ __forceinline__ void map_put(uint8_t *m, int k, int tw, uint8_t v)
+{
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(map_addr(smem_u32(m), k, tw)), "r"((uint32_t)v) : "memory");
+}
 
 template <int W1, int W2, bool LORDER, bool XORWOW>
 struct Chain {
@@ -306,9 +324,9 @@ struct Chain {
   {
     int d = 0;
     const int fmask = from >= 0 ? -1 : 0, tmask = to >= 0 ? -1 : 0;
-    const uint2 *qrow = v.qcell + i * v.n1;
-    const uint2 *frow = v.ecell + (from & fmask) * v.n2;
-    const uint2 *trow = v.ecell + (to & tmask) * v.n2;
+    const uint32_t qrow = smem_u32(v.qcell) + (uint32_t)(i * v.n1) * 8u;          // row base addresses, hoisted by hand
+    const uint32_t frow = smem_u32(v.ecell) + (uint32_t)((from & fmask) * v.n2) * 8u;
+    const uint32_t trow = smem_u32(v.ecell) + (uint32_t)((to & tmask) * v.n2) * 8u;
 #pragma unroll
     for (int w = 0; w < W1; w++) {
       uint32_t b = mq[w];
@@ -317,8 +335,8 @@ struct Chain {
         const int k = 32 * w + __ffs(b) - 1;
         b &= b - 1u;
         const int l = map_get(v.smap, k, v.tw);
-        const uint2 q = qrow[k];
-        const uint2 ef = frow[l], et = trow[l];
+        const uint2 q = lds64(qrow + (uint32_t)k * 8u);
+        const uint2 ef = lds64(frow + (uint32_t)l * 8u), et = lds64(trow + (uint32_t)l * 8u);
         d += (gated(q, et) & tmask) - (gated(q, ef) & fmask);
       }
     }
