@@ -181,8 +181,8 @@ __device__ __forceinline__ float unit_from_bits(uint32_t x)
 // (u - 1.1e-7) * n in double, truncated (kernel.cu:67, :1042, :710)
 __device__ __forceinline__ int scaled_index(float u, int n)
 {
-  double x = ((double)u - 1.1e-7) * (double)n;
-  return x <= 0.0 ? 0 : (int)x;
+  // u >= 2^-33, so the product is > -1 and the truncating conversion already maps the negative sliver to 0
+  return (int)(((double)u - 1.1e-7) * (double)n);
 }
 
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
@@ -324,9 +324,10 @@ struct Chain {
   {
     int d = 0;
     const int fmask = from >= 0 ? -1 : 0, tmask = to >= 0 ? -1 : 0;
-    const uint32_t qrow = smem_u32(v.qcell) + (uint32_t)(i * v.n1) * 8u;          // row base addresses, hoisted by hand
-    const uint32_t frow = smem_u32(v.ecell) + (uint32_t)((from & fmask) * v.n2) * 8u;
-    const uint32_t trow = smem_u32(v.ecell) + (uint32_t)((to & tmask) * v.n2) * 8u;
+    uint32_t qrow = smem_u32(v.qcell) + (uint32_t)(i * v.n1) * 8u;                // row base addresses, hoisted by hand
+    uint32_t frow = smem_u32(v.ecell) + (uint32_t)((from & fmask) * v.n2) * 8u;
+    uint32_t trow = smem_u32(v.ecell) + (uint32_t)((to & tmask) * v.n2) * 8u;
+    asm volatile("" : "+r"(qrow), "+r"(frow), "+r"(trow));       // keep the compiler from re-folding them into the loop
 #pragma unroll
     for (int w = 0; w < W1; w++) {
       uint32_t b = mq[w];
