@@ -67,6 +67,13 @@ def _load() -> C.CDLL:
         "sats_searcher_launch_count": (C.c_longlong, [vp]),
         "sats_searcher_get_xorwow": (ci, [vp, vp]), "sats_searcher_reset_xorwow": (ci, [vp, C.c_uint64]),
         "sats_device_count": (ci, []),
+        "sats_search_topk": (ci, [vp, ci, vp, vp]),
+        "sats_results_parse": (ci, [cs, C.c_size_t, P(vp)]), "sats_results_free": (None, [vp]),
+        "sats_results_blocks": (ci, [vp]), "sats_results_query": (cs, [vp, ci]), "sats_results_dbfile": (cs, [vp, ci]),
+        "sats_results_flags": (ci, [vp, ci, P(ci)]), "sats_results_rows": (ci, [vp, ci]),
+        "sats_results_row": (ci, [vp, ci, ci, cs, P(C.c_int32), P(C.c_double), P(C.c_double), P(C.c_double)]),
+        "sats_results_map": (ci, [vp, ci, ci, vp, ci]),
+        "sats_roc_auc": (C.c_double, [vp, vp, ci]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)          # AttributeError here = the library does not export what sats.h declares
@@ -315,6 +322,14 @@ class Searcher:
     def sync(self):
         _check(lib().sats_searcher_sync(self._h))
 
+    def topk(self, k: int):
+        """After launch(): device-side selection -> (index int32 [q, k] original db indices, scores int32 [q, k])."""
+        q = self._qcount
+        idx = np.full((q, k), -1, np.int32)
+        sc = np.full((q, k), np.iinfo(np.int32).min, np.int32)
+        _check(lib().sats_search_topk(self._h, k, idx.ctypes.data, sc.ctypes.data))
+        return idx, sc
+
     def xorwow_states(self) -> np.ndarray:
         st = np.zeros((128 * 128, 6), np.uint32)
         _check(lib().sats_searcher_get_xorwow(self._h, st.ctypes.data))
@@ -322,3 +337,38 @@ class Searcher:
 
     def reset_xorwow(self, seed: int = 1234):
         _check(lib().sats_searcher_reset_xorwow(self._h, seed))
+
+
+def parse_results(text: bytes | str):
+    """Five-column output -> list of blocks: dict(query, dbfile, ltype, lorder, lsoln, names, scores, norm2, z, p, maps)."""
+    b = text.encode() if isinstance(text, str) else text
+    h = C.c_void_p()
+    _check(lib().sats_results_parse(b, len(b), C.byref(h)))
+    out = []
+    try:
+        for k in range(lib().sats_results_blocks(h)):
+            flags = (C.c_int * 3)()
+            lib().sats_results_flags(h, k, flags)
+            n = lib().sats_results_rows(h, k)
+            blk = dict(query=lib().sats_results_query(h, k).decode().strip(), dbfile=lib().sats_results_dbfile(h, k).decode().strip(),
+                       ltype=bool(flags[0]), lorder=bool(flags[1]), lsoln=bool(flags[2]), names=[],
+                       scores=np.zeros(n, np.int32), norm2=np.zeros(n), z=np.zeros(n), p=np.zeros(n), maps=[])
+            name = C.create_string_buffer(9)
+            sc = C.c_int32(); a = C.c_double(); z = C.c_double(); p = C.c_double()
+            pairs = np.zeros(2 * MAXDIM, np.int32)
+            for r in range(n):
+                lib().sats_results_row(h, k, r, name, C.byref(sc), C.byref(a), C.byref(z), C.byref(p))
+                blk["names"].append(name.value.decode())
+                blk["scores"][r], blk["norm2"][r], blk["z"][r], blk["p"][r] = sc.value, a.value, z.value, p.value
+                m = lib().sats_results_map(h, k, r, pairs.ctypes.data, MAXDIM)
+                blk["maps"].append(pairs[:2 * m].reshape(m, 2).copy())
+            out.append(blk)
+    finally:
+        lib().sats_results_free(h)
+    return out
+
+
+def roc_auc(scores, positive) -> float:
+    s = np.ascontiguousarray(scores, np.float64)
+    y = np.ascontiguousarray(positive, np.uint8)
+    return lib().sats_roc_auc(s.ctypes.data, y.ctypes.data, len(s))

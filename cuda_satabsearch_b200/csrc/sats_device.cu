@@ -73,6 +73,7 @@ struct sats_searcher {
   int32_t *h_scores = nullptr; int8_t *h_maps = nullptr;
   size_t score_cap = 0, map_cap = 0;
   int last_q = 0, last_lsoln = 0;
+  int32_t *d_topk = nullptr, *h_topk = nullptr; size_t topk_cap = 0;
   long long launches = 0;
   bool attr_done = false;
 };
@@ -214,7 +215,7 @@ extern "C" void sats_searcher_free(sats_searcher *s)
   if (s->stream) cudaStreamSynchronize(s->stream);
   cudaFree(s->d_blobs); cudaFree(s->d_blob_off); cudaFree(s->d_blob_bytes); cudaFree(s->d_accept); cudaFree(s->d_xw);
   cudaFree(s->d_pool_list); cudaFree(s->d_xw_blocks); cudaFree(s->d_qblobs); cudaFree(s->d_qoff); cudaFree(s->d_qbytes);
-  cudaFree(s->d_scores); cudaFree(s->d_maps);
+  cudaFree(s->d_scores); cudaFree(s->d_maps); cudaFree(s->d_topk); cudaFreeHost(s->h_topk);
   cudaFreeHost(s->h_qstage); cudaFreeHost(s->h_scores); cudaFreeHost(s->h_maps);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
@@ -518,6 +519,164 @@ extern "C" int sats_search_collect(sats_searcher *s, int32_t *scores, int32_t *m
         const int8_t *row = s->h_maps + ((size_t)q * D + kpos) * SATS_K_MAPROW;
         int32_t *dst = maps + o * SATS_MAP_STRIDE;
         for (int i = 0; i < n1; i++) dst[i] = row[i];
+      }
+    }
+  }
+  return SATS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ top-k
+// One CTA per query slot selects the k best-scoring entries of that query on the device, so only k (position, score)
+// pairs cross PCIe instead of one score per database entry.  Scores are small integers, so an exact counting select
+// does it: block max, histogram of (max - score), threshold bin, then an ordered pick -- everything above the threshold
+// plus the first `need` entries AT the threshold in device order (= decreasing structure order, then file order).
+#define SATS_TOPK_THREADS 1024
+#define SATS_TOPK_BINS 4096
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *scratch, int *total)
+{
+  // Hillis-Steele over SATS_TOPK_THREADS values in shared memory
+  const int t = threadIdx.x;
+  scratch[t] = v;
+  __syncthreads();
+  for (int off = 1; off < SATS_TOPK_THREADS; off <<= 1) {
+    int add = t >= off ? scratch[t - off] : 0;
+    __syncthreads();
+    scratch[t] += add;
+    __syncthreads();
+  }
+  const int incl = scratch[t];
+  *total = scratch[SATS_TOPK_THREADS - 1];
+  __syncthreads();
+  return incl - v;
+}
+
+__global__ void __launch_bounds__(SATS_TOPK_THREADS)
+sats_topk_kernel(const int32_t *scores, int stride, int count, int k, int32_t *out_pos, int32_t *out_score, int32_t *out_n)
+{
+  __shared__ int hist[SATS_TOPK_BINS];
+  __shared__ int scratch[SATS_TOPK_THREADS];
+  __shared__ int s_max, s_min, s_thr, s_need;
+  const int q = blockIdx.x, t = threadIdx.x;
+  const int32_t *row = scores + (size_t)q * stride;
+  const int32_t none = (int32_t)0x80808080;
+  // (a) maximum over computed entries
+  int mx = INT_MIN, mn = INT_MAX;
+  for (int e = t; e < count; e += SATS_TOPK_THREADS) { int v = row[e]; if (v != none) { mx = max(mx, v); mn = min(mn, v); } }
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  if ((t & 31) == 0) { scratch[t >> 5] = mx; scratch[32 + (t >> 5)] = mn; }
+  for (int b = t; b < SATS_TOPK_BINS; b += SATS_TOPK_THREADS) hist[b] = 0;
+  __syncthreads();
+  if (t == 0) {
+    int m = INT_MIN, n = INT_MAX;
+    for (int w = 0; w < SATS_TOPK_THREADS / 32; w++) { m = max(m, scratch[w]); n = min(n, scratch[32 + w]); }
+    s_max = m; s_min = n;
+  }
+  __syncthreads();
+  mx = s_max;
+  // (b) histogram of max - score (scores further than BINS-1 below the maximum share the last bin)
+  for (int e = t; e < count; e += SATS_TOPK_THREADS) {
+    int v = row[e];
+    if (v != none) atomicAdd(&hist[min(mx - v, SATS_TOPK_BINS - 1)], 1);
+  }
+  __syncthreads();
+  // (c) threshold bin: the first bin at which the running count reaches k
+  if (t == 0) {
+    int run = 0, thr = SATS_TOPK_BINS - 1;
+    for (int b = 0; b < SATS_TOPK_BINS; b++) { if (run + hist[b] >= k) { thr = b; break; } run += hist[b]; }
+    s_thr = thr;
+    s_need = k - run;              // how many entries of the threshold bin are still wanted (may exceed what exists)
+  }
+  __syncthreads();
+  const int thr = s_thr, need = s_need;
+  // scores spread over more than BINS values and the cut falls into the shared last bin: cannot order it here
+  if (thr == SATS_TOPK_BINS - 1 && (long long)mx - (long long)s_min >= SATS_TOPK_BINS - 1) {
+    if (t == 0) out_n[q] = -1;
+    return;
+  }
+  // (d) ordered pick: thread t owns a contiguous chunk of the (device-ordered) entries
+  const int chunk = (count + SATS_TOPK_THREADS - 1) / SATS_TOPK_THREADS;
+  const int lo = min(count, t * chunk), hi = min(count, lo + chunk);
+  int nsel = 0, ntie = 0;
+  for (int e = lo; e < hi; e++) {
+    int v = row[e];
+    if (v == none) continue;
+    int b = min(mx - v, SATS_TOPK_BINS - 1);
+    nsel += b < thr;
+    ntie += b == thr;
+  }
+  int total;
+  const int ties_before = block_exclusive_scan(ntie, scratch, &total);
+  const int quota = max(0, min(ntie, need - ties_before));
+  const int base = block_exclusive_scan(nsel + quota, scratch, &total);
+  if (t == 0) out_n[q] = min(total, k);
+  int w = base, taken = 0;
+  for (int e = lo; e < hi; e++) {
+    int v = row[e];
+    if (v == none) continue;
+    int b = min(mx - v, SATS_TOPK_BINS - 1);
+    bool take = b < thr || (b == thr && taken < quota);
+    if (b == thr && taken < quota) taken++;
+    if (take && w < k) { out_pos[(size_t)q * k + w] = e; out_score[(size_t)q * k + w] = v; w++; }
+  }
+}
+
+extern "C" int sats_search_topk(sats_searcher *s, int k, int32_t *index_out, int32_t *score_out)
+{
+  if (!s || !index_out || !score_out || k < 1) return sats_fail(SATS_ERR_ARG, "sats_search_topk: bad argument");
+  if (s->last_q < 1) return sats_fail(SATS_ERR_ARG, "sats_search_topk: no search has been launched");
+  CK(cudaSetDevice(s->device));
+  const int D = (int)s->sorted_orig.size(), Q = s->last_q;
+  size_t n = (size_t)Q * k;
+  if (n > s->topk_cap) {
+    cudaFree(s->d_topk); cudaFreeHost(s->h_topk);
+    s->d_topk = nullptr; s->h_topk = nullptr; s->topk_cap = 0;
+    CK(cudaMalloc(&s->d_topk, (2 * n + Q) * 4));
+    CK(cudaMallocHost(&s->h_topk, (2 * n + Q) * 4));
+    s->topk_cap = n;
+  }
+  int32_t *d_pos = s->d_topk, *d_sc = s->d_topk + n, *d_n = s->d_topk + 2 * n;
+  sats_topk_kernel<<<Q, SATS_TOPK_THREADS, 0, s->stream>>>(s->d_scores, std::max(1, D), D, k, d_pos, d_sc, d_n);
+  CK(cudaGetLastError());
+  s->launches++;
+  CK(cudaMemcpyAsync(s->h_topk, s->d_topk, (2 * n + Q) * 4, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  const int32_t *h_pos = s->h_topk, *h_sc = s->h_topk + n, *h_n = s->h_topk + 2 * n;
+  std::vector<int> order((size_t)k);
+  std::vector<int32_t> rowbuf, rowpos;
+  for (int q = 0; q < Q; q++) {
+    int got = h_n[q];
+    if (got < 0) {
+      // rare fallback (see kernel): select this query's row on the host with the same ordering rule
+      rowbuf.resize((size_t)D);
+      CK(cudaMemcpy(rowbuf.data(), s->d_scores + (size_t)q * std::max(1, D), (size_t)D * 4, cudaMemcpyDeviceToHost));
+      rowpos.clear();
+      for (int e = 0; e < D; e++) if (rowbuf[e] != kScoreSentinel) rowpos.push_back(e);
+      got = std::min<int>(k, (int)rowpos.size());
+      std::partial_sort(rowpos.begin(), rowpos.begin() + got, rowpos.end(), [&](int a, int b) {
+        if (rowbuf[a] != rowbuf[b]) return rowbuf[a] > rowbuf[b];
+        return a < b;
+      });
+      for (int i = 0; i < k; i++) {
+        index_out[(size_t)q * k + i] = i < got ? s->sorted_orig[rowpos[i]] : -1;
+        score_out[(size_t)q * k + i] = i < got ? rowbuf[rowpos[i]] : INT_MIN;
+      }
+      continue;
+    }
+    std::iota(order.begin(), order.begin() + got, 0);
+    std::sort(order.begin(), order.begin() + got, [&](int a, int b) {
+      int sa = h_sc[(size_t)q * k + a], sb = h_sc[(size_t)q * k + b];
+      if (sa != sb) return sa > sb;
+      return h_pos[(size_t)q * k + a] < h_pos[(size_t)q * k + b];
+    });
+    for (int i = 0; i < k; i++) {
+      if (i < got) {
+        index_out[(size_t)q * k + i] = s->sorted_orig[h_pos[(size_t)q * k + order[i]]];
+        score_out[(size_t)q * k + i] = h_sc[(size_t)q * k + order[i]];
+      } else {
+        index_out[(size_t)q * k + i] = -1;
+        score_out[(size_t)q * k + i] = INT_MIN;
       }
     }
   }

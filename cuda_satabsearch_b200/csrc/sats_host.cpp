@@ -534,3 +534,111 @@ extern "C" void sats_params_default(sats_params *p)
   p->pool_threshold = SATS_MAXDIM_GPU;
   p->seed = SATS_REF_SEED;
 }
+
+// ------------------------------------------------------------------------------------------ result reader
+struct sats_results {
+  struct Row { char name[9]; int32_t score; double norm2, z, p; std::vector<int32_t> pairs; };
+  struct Block { std::string query, dbfile; int flags[3] = {1, 1, 0}; std::vector<Row> rows; };
+  std::vector<Block> blocks;
+};
+
+extern "C" int sats_results_parse(const char *text, size_t len, sats_results **out)
+{
+  if (!text || !out) return sats_fail(SATS_ERR_ARG, "sats_results_parse: null argument");
+  sats_results *r = new sats_results();
+  Cursor c{text, text + len};
+  const char *b, *e;
+  int lineno = 0;
+  while (c.line(b, e)) {
+    lineno++;
+    std::string ln(b, e);
+    while (!ln.empty() && (ln.back() == '\r' || ln.back() == ' ')) ln.pop_back();
+    if (ln.empty()) continue;
+    if (ln[0] == '#') {
+      char f[3];
+      if (sscanf(ln.c_str(), "# cudaSaTabsearch LTYPE = %c LORDER = %c LSOLN = %c", &f[0], &f[1], &f[2]) == 3) {
+        r->blocks.emplace_back();
+        for (int i = 0; i < 3; i++) r->blocks.back().flags[i] = f[i] == 'T';
+      } else if (!r->blocks.empty() && ln.compare(0, 13, "# QUERY ID = ") == 0) {
+        r->blocks.back().query = ln.substr(13);
+      } else if (!r->blocks.empty() && ln.compare(0, 11, "# DBFILE = ") == 0) {
+        r->blocks.back().dbfile = ln.substr(11);
+      }
+      continue;
+    }
+    if (r->blocks.empty()) r->blocks.emplace_back();       // headerless output (e.g. filtered through grep -v '#')
+    sats_results::Row row;
+    char nm[64];
+    int a, bb;
+    char extra;
+    if (sscanf(ln.c_str(), "%63s %d %lf %lf %lf", nm, &row.score, &row.norm2, &row.z, &row.p) == 5) {
+      memset(row.name, 0, 9);
+      strncpy(row.name, nm, 8);
+      r->blocks.back().rows.push_back(row);
+    } else if (sscanf(ln.c_str(), "%d %d %c", &a, &bb, &extra) == 2 && !r->blocks.back().rows.empty()) {
+      r->blocks.back().rows.back().pairs.push_back(a);
+      r->blocks.back().rows.back().pairs.push_back(bb);
+    } else {
+      delete r;
+      return sats_fail(SATS_ERR_PARSE, "result line %d not understood: %.60s", lineno, ln.c_str());
+    }
+  }
+  *out = r;
+  return SATS_OK;
+}
+
+extern "C" void sats_results_free(sats_results *r) { delete r; }
+extern "C" int sats_results_blocks(const sats_results *r) { return r ? (int)r->blocks.size() : 0; }
+static const sats_results::Block *blk(const sats_results *r, int b) { return (r && b >= 0 && b < (int)r->blocks.size()) ? &r->blocks[b] : nullptr; }
+extern "C" const char *sats_results_query(const sats_results *r, int b) { return blk(r, b) ? blk(r, b)->query.c_str() : ""; }
+extern "C" const char *sats_results_dbfile(const sats_results *r, int b) { return blk(r, b) ? blk(r, b)->dbfile.c_str() : ""; }
+extern "C" int sats_results_flags(const sats_results *r, int b, int flags_tf[3])
+{
+  if (!blk(r, b) || !flags_tf) return sats_fail(SATS_ERR_ARG, "sats_results_flags: bad block %d", b);
+  for (int i = 0; i < 3; i++) flags_tf[i] = blk(r, b)->flags[i];
+  return SATS_OK;
+}
+extern "C" int sats_results_rows(const sats_results *r, int b) { return blk(r, b) ? (int)blk(r, b)->rows.size() : SATS_ERR_ARG; }
+extern "C" int sats_results_row(const sats_results *r, int b, int row, char name[9], int32_t *score, double *norm2, double *z,
+                                double *pvalue)
+{
+  const sats_results::Block *k = blk(r, b);
+  if (!k || row < 0 || row >= (int)k->rows.size()) return sats_fail(SATS_ERR_ARG, "sats_results_row: bad block/row %d/%d", b, row);
+  const sats_results::Row &x = k->rows[row];
+  if (name) memcpy(name, x.name, 9);
+  if (score) *score = x.score;
+  if (norm2) *norm2 = x.norm2;
+  if (z) *z = x.z;
+  if (pvalue) *pvalue = x.p;
+  return SATS_OK;
+}
+extern "C" int sats_results_map(const sats_results *r, int b, int row, int32_t *pairs, int cap)
+{
+  const sats_results::Block *k = blk(r, b);
+  if (!k || row < 0 || row >= (int)k->rows.size()) return sats_fail(SATS_ERR_ARG, "sats_results_map: bad block/row %d/%d", b, row);
+  const std::vector<int32_t> &p = k->rows[row].pairs;
+  int n = (int)p.size() / 2;
+  for (int i = 0; i < n && i < cap && pairs; i++) { pairs[2 * i] = p[2 * i]; pairs[2 * i + 1] = p[2 * i + 1]; }
+  return n;
+}
+
+extern "C" double sats_roc_auc(const double *score, const uint8_t *positive, int n)
+{
+  if (!score || !positive || n < 2) return NAN;
+  std::vector<int> idx((size_t)n);
+  std::iota(idx.begin(), idx.end(), 0);
+  std::sort(idx.begin(), idx.end(), [&](int a, int b) { return score[a] < score[b]; });
+  // rank-sum with mid-ranks for ties
+  double ranksum = 0.0;
+  long long npos = 0;
+  for (int i = 0; i < n;) {
+    int j = i;
+    while (j < n && score[idx[j]] == score[idx[i]]) j++;
+    double midrank = 0.5 * ((i + 1) + j);
+    for (int t = i; t < j; t++) if (positive[idx[t]]) { ranksum += midrank; npos++; }
+    i = j;
+  }
+  long long nneg = n - npos;
+  if (npos == 0 || nneg == 0) return NAN;
+  return (ranksum - 0.5 * (double)npos * (double)(npos + 1)) / ((double)npos * (double)nneg);
+}

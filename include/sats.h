@@ -110,6 +110,25 @@ size_t sats_format_block(char *buf, size_t cap, const char *query_id, int query_
                          const char *dbfile, int lorder, int lsoln, const sats_db *db,
                          const int32_t *index, int count, const int32_t *scores, const int32_t *maps);
 
+/* ---- reading result files --------------------------------------------------------------
+ * Parser for the five-column stdout grammar above ('#' header lines, rows, optional "%3d %3d" map pairs): what the
+ * reference's tooling consumes (scripts/tsevalutils.py:223-296, scripts/parsessemap.py:43-147).  A block is one
+ * (query, pool) section.                                                                                          */
+typedef struct sats_results sats_results;
+int sats_results_parse(const char *text, size_t len, sats_results **out);
+void sats_results_free(sats_results *r);
+int sats_results_blocks(const sats_results *r);
+const char *sats_results_query(const sats_results *r, int block);
+const char *sats_results_dbfile(const sats_results *r, int block);
+int sats_results_flags(const sats_results *r, int block, int flags_tf[3]);
+int sats_results_rows(const sats_results *r, int block);
+int sats_results_row(const sats_results *r, int block, int row, char name[9], int32_t *score, double *norm2,
+                     double *zscore, double *pvalue);
+/* SSE map of a row (LSOLN=T): returns the number of pairs and copies up to cap 1-based (query, db) pairs          */
+int sats_results_map(const sats_results *r, int block, int row, int32_t *pairs, int cap);
+/* ROC AUC of scores against binary labels, ties counted one half (Mann-Whitney U / (P*N)); NaN if a class is empty */
+double sats_roc_auc(const double *score, const uint8_t *positive, int n);
+
 /* ---- search (replaces sa_tabsearch_gpu / _noshared / _host, cudaSaTabsearch_kernel.h:15-64,
  *      plus copyQueryToConstantMemory cudaSaTabsearch.cu:486-558 and init_rng :258-264) --------- */
 
@@ -188,6 +207,12 @@ int sats_search_upload(sats_searcher *s, const sats_db *queries, int qfirst, int
 int sats_search_launch(sats_searcher *s, const sats_params *params, uint32_t query_index_base,
                        float *elapsed_ms);
 int sats_search_collect(sats_searcher *s, int32_t *scores, int32_t *maps);
+/* after sats_search_launch(), the k best-scoring entries of every query slot, selected ON THE DEVICE
+ * (exact counting select over the integer scores) so that only k (index, score) pairs per query are copied back
+ * instead of one score per database entry.  Rows of k: score descending; ties by decreasing structure order, then
+ * file order (the device order).  index_out receives ORIGINAL db indices (-1 padding), score_out the raw scores
+ * (INT32_MIN padding).  A sharded search returns each shard's local top-k; merge the shards on the host.          */
+int sats_search_topk(sats_searcher *s, int k, int32_t *index_out, int32_t *score_out);
 int sats_searcher_sync(sats_searcher *s);
 /* kernels launched by this searcher since creation (for the bench's gpu_launches claim)          */
 long long sats_searcher_launch_count(const sats_searcher *s);

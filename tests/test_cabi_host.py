@@ -157,3 +157,35 @@ def test_select_and_from_structures_roundtrip():
     sub = db.select([5, 0, 19])
     assert sub.names() == [ref[5].name, ref[0].name, ref[19].name]
     assert np.array_equal(sub.get(2)[1], ref[19].dmat)
+
+
+def test_results_reader_and_auc(golden):
+    """the five-column output reader round-trips what the formatter prints, and sats_roc_auc equals
+    the Mann-Whitney statistic."""
+    case = golden["cases"]["d1ubia_test1_default"]          # LSOLN=T: rows + map pairs
+    db = S.Database.read_packed(GOLDEN / "test1.satsdb")
+    blk = case["blocks"][0]
+    maps = np.full((1, S.MAP_STRIDE), -1, np.int32)
+    for k, j in blk["maps"][0]:
+        maps[0, k - 1] = j - 1
+    text = db.format_block("D1UBIA_", 8, case["dbfile"], True, True, np.array(blk["scores"], np.int32), maps)
+    case2 = golden["cases"]["d2phlb1_small_r128"]
+    db2 = S.Database.read_packed(GOLDEN / "small586.satsdb")
+    text += db2.format_block("D2PHLB1", 19, case2["dbfile"], True, False, np.array(case2["blocks"][0]["scores"], np.int32))
+    out = S.parse_results(text)
+    assert [b["query"] for b in out] == ["D1UBIA_", "D2PHLB1"]
+    assert out[0]["lsoln"] and not out[1]["lsoln"] and out[0]["dbfile"] == case["dbfile"]
+    assert out[0]["names"] == ["d1ndda_"] and out[0]["scores"].tolist() == [54]
+    assert out[0]["maps"][0].tolist() == [[k, k] for k in range(1, 9)]
+    assert out[1]["names"] == case2["blocks"][0]["names"] and out[1]["scores"].tolist() == case2["blocks"][0]["scores"]
+    n2s, z, p = stats(54, 8, 8)
+    assert abs(out[0]["norm2"][0] - n2s) < 1e-5 and abs(out[0]["z"][0] - z) < 1e-4
+    with pytest.raises(S.SatsError, match="not understood"):
+        S.parse_results("name 1 2\n")
+    rng = np.random.default_rng(3)
+    score = rng.integers(0, 12, 400).astype(float)
+    y = rng.random(400) < 0.2
+    pos, neg = score[y], score[~y]
+    want = ((pos[:, None] > neg[None, :]).sum() + 0.5 * (pos[:, None] == neg[None, :]).sum()) / (len(pos) * len(neg))
+    assert abs(S.roc_auc(score, y) - want) < 1e-12
+    assert np.isnan(S.roc_auc(score, np.zeros(400, bool)))

@@ -148,3 +148,34 @@ def test_production_mode_agrees_statistically_with_reference(base, fixtures, gol
     ref_mean = np.mean([x.mean() for x in ref_runs]); our_mean = np.mean([x.mean() for x in our_runs])
     assert abs(our_mean - ref_mean) < 0.1, (our_mean, ref_mean)
     assert np.corrcoef(np.mean(our_runs, 0), np.mean(ref_runs, 0))[0, 1] > 0.985
+
+
+def test_device_topk_matches_host_selection(base, fixtures):
+    """device-side top-k (counting select) == host selection with the same rule: score descending,
+    ties by decreasing structure order then file order.  Includes a query that finds itself (a score thousands above
+    the rest: the wide-range fallback) and k larger than the database."""
+    db = base.bootstrap(20000, 7, True)
+    qidx = np.array([3, 19999, 12000], np.int32)             # tiny, largest, mid-size structures of the db itself
+    queries = db.select(qidx)
+    big = fixtures["queries_by_name"]["d1twfa_"]
+    qs = as_db(structures_of(queries, range(3)) + [big, fixtures["queries_by_name"]["D2PHLB1"]])
+    sr = S.Searcher(db, 0)
+    p = S.default_params(lorder=1, lsoln=0, restarts=128, seed=11)
+    sr.upload(qs)
+    sr.launch(p)
+    full, _ = sr.collect()
+    orders = db.orders()
+    devpos = np.empty(len(db), np.int64)
+    devpos[np.argsort(-orders, kind="stable")] = np.arange(len(db))          # device order of every original index
+    for k in (1, 10, 500):
+        idx, sc = sr.topk(k)
+        for q in range(len(qs)):
+            want = np.lexsort((devpos, -full[q].astype(np.int64)))[:k]
+            assert idx[q].tolist() == want.tolist(), (k, q)
+            assert sc[q].tolist() == full[q][want].tolist()
+    small = S.Searcher(db.select(np.arange(50, dtype=np.int32)), 0)
+    small.upload(qs, 4, 1)
+    small.launch(p)
+    idx, sc = small.topk(64)
+    assert (idx[0, :50] >= 0).all() and (idx[0, 50:] == -1).all() and sorted(idx[0, :50].tolist()) == list(range(50))
+    sr.close(); small.close()
