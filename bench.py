@@ -274,6 +274,8 @@ def ours(args):
                     sm_mhz, peak_kind, prof.get("capture", "no capture")),
         "issue": {"warp_inst_per_move": prof.get("warp_inst_per_move"),
                   "avg_active_threads_per_inst": prof.get("avg_active_threads_per_inst"),
+                  "ncu_issue_active_pct": prof.get("issue_active_pct_time_weighted"),
+                  "ncu_smem_wavefront_pct_of_peak": prof.get("smem_wavefront_pct_of_peak_time_weighted"),
                   "achieved_warp_inst_per_s": moves * prof["warp_inst_per_move"] if prof.get("warp_inst_per_move") else None,
                   "peak_warp_inst_per_s": n_gpus * SM_COUNT * ISSUE_SLOTS_PER_CLK_PER_SM * sm_mhz * 1e6,
                   "frac": (moves * prof["warp_inst_per_move"] / (n_gpus * SM_COUNT * ISSUE_SLOTS_PER_CLK_PER_SM * sm_mhz * 1e6))
