@@ -136,6 +136,27 @@ def run_reference_cpu(S, db, per_proc: int, procs: int):
     return per_proc * procs / slowest, {"wall_s": wall, "slowest_search_s": slowest}
 
 
+def run_reference_gpu(S, db, count: int):
+    """The reference's own GPU kernel (sa_tabsearch_gpu<<<128,128>>>, cuRAND XORWOW, --use_fast_math) rebuilt for sm_100a
+    and run on this box against a size-stratified sample, timed by its own stderr timer around the kernel."""
+    sample = stratified_sample(S, db, count)
+    qs = query_db(S)
+    with tempfile.TemporaryDirectory() as td:
+        qs.write_ascii(os.path.join(td, "q.ascii"))
+        sample.write_ascii(os.path.join(td, "db.ascii"))
+        Path(td, "in").write_text("db.ascii\nT T F\n" + Path(td, "q.ascii").read_text())
+        pr = subprocess.run([str(REF_BIN), "-r", str(RESTARTS)], stdin=open(os.path.join(td, "in")), stdout=subprocess.DEVNULL,
+                            stderr=subprocess.PIPE, cwd=td, text=True, timeout=600)
+    if pr.returncode != 0:
+        return None
+    ms = [float(x) for x in re.findall(r"GPU execution time ([0-9.]+) ms", pr.stderr)]
+    if not ms:
+        return None
+    return {"value": count / (sum(ms) / 1e3), "unit": "structures/s", "kernel_ms": sum(ms),
+            "sample": "%d structures (size-stratified sample of the 100k synthetic db), the reference's sa_tabsearch_gpu<<<128,128>>> "
+                      "rebuilt with -arch=sm_100a and its own --use_fast_math, timed by its own 'GPU execution time'" % count}
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -292,6 +313,12 @@ def ours(args):
         cpu = {"value": v, "unit": "structures/s", "cores": 1, "kind": "reference",
                "sample": "4000 structures (size-stratified sample of the 100k synthetic db), reference -c path, one "
                          "process; rate = structures / its own 'host execution time' (%.1f s)" % det["slowest_search_s"]}
+    ref_gpu = None
+    if n_gpus == 1 and REF_BIN.exists() and not args.no_cpu:
+        try:
+            ref_gpu = run_reference_gpu(S, db, 20000)
+        except Exception as exc:                       # never let the side measurement break the bench line
+            ref_gpu = {"error": str(exc)[:200]}
     line = {
         "metric": METRIC, "value": value, "unit": "structures/s", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -300,6 +327,7 @@ def ours(args):
         "e2e": {"value": e2e_value, "unit": "structures/s", "h2d_bytes_per_step": int(n_gpus * (128 + 8 * 19 * 19 + 12)),
                 "d2h_bytes_per_step": int(4 * DB_SIZE), "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+        "reference_gpu_same_box": ref_gpu,
         "local_entries_rank0": n_local,
     }
     print(json.dumps(line))
