@@ -189,3 +189,17 @@ def test_results_reader_and_auc(golden):
     want = ((pos[:, None] > neg[None, :]).sum() + 0.5 * (pos[:, None] == neg[None, :]).sum()) / (len(pos) * len(neg))
     assert abs(S.roc_auc(score, y) - want) < 1e-12
     assert np.isnan(S.roc_auc(score, np.zeros(400, bool)))
+
+
+def test_c_consumer_links_and_runs(tmp_path):
+    """include/sats.h must be plain C and libsats must link from a C program (the reference's host code is C)."""
+    exe = tmp_path / "cabi_smoke"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", str(REPO / "include"),
+                    str(REPO / "tests" / "cabi_smoke.c"), "-o", str(exe), "-L", str(S.LIB_PATH.parent), "-lsats",
+                    "-Wl,-rpath," + str(S.LIB_PATH.parent), "-lm"], check=True, capture_output=True)
+    p = subprocess.run([str(exe), str(GOLDEN / "small586.satsdb")], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, (p.returncode, p.stdout, p.stderr)
+    first = p.stdout.split("\n")[0].split()
+    assert first[:2] == ["586", "67"] and abs(float(first[2]) - 6.75) < 1e-9 and abs(float(first[3]) - 11.7853) < 1e-3
+    if S.device_count() == 0:
+        assert "no CUDA device" in p.stdout

@@ -89,3 +89,17 @@ def test_cli_reads_packed_cache(tmp_path, fixtures):
         assert p.returncode == 0
         outs.append([ln for ln in p.stdout.decode().split("\n") if not ln.startswith("# DBFILE")])
     assert outs[0] == outs[1]
+
+
+@pytest.mark.skipif(S.device_count() < 2, reason="needs two GPUs")
+def test_cli_multi_gpu_output_is_identical(tmp_path, fixtures):
+    """-g 2 shards the database over two GPUs (cost-weighted partition); Philox chains are keyed by original entry
+    index, so stdout must be byte-identical to the single-GPU run."""
+    ents = fixtures["small586"]
+    qs = [fixtures["queries_by_name"][n] for n in ("D2PHLB1", "SHEETBC")]
+    write_ascii_db(tmp_path / "db.ascii", ents)
+    write_query_input(tmp_path / "q.input", "db.ascii", True, True, qs)
+    one = run([CLI, "-r", 128, "-g", 1], tmp_path / "q.input", tmp_path)
+    two = run([CLI, "-r", 128, "-g", 2], tmp_path / "q.input", tmp_path)
+    assert one.returncode == 0 and two.returncode == 0, two.stderr.decode()[-1000:]
+    assert one.stdout == two.stdout and len(one.stdout) > 10000
