@@ -104,22 +104,34 @@ __device__ __forceinline__ void team_sync(int team, int tw)
 }
 
 // ------------------------------------------------------------------------------------------------ bit sets
+// Bit b of a W-word mask, as seen from word w: 1 << (b - 32w) when that lands inside the word, else 0.  PTX shl.b32
+// clamps shift amounts above 31 to a zero result, and a negative offset is a huge unsigned amount, so one shift does it
+// -- and, unlike "if ((b >> 5) == w)", it cannot be turned into a dynamically indexed (local-memory) array access.
+__device__ __forceinline__ uint32_t bit_in_word(int b, int w)
+{
+  uint32_t r;
+  asm("shl.b32 %0, 1, %1;" : "=r"(r) : "r"((uint32_t)(b - 32 * w)));
+  return r;
+}
 template <int W> __device__ __forceinline__ bool bit_test(const uint32_t (&m)[W], int b)
 {
-  uint32_t word = m[0];
+  if (W == 1) return (m[0] >> (b & 31)) & 1u;
+  uint32_t hit = 0u;
 #pragma unroll
-  for (int w = 1; w < W; w++) if ((b >> 5) == w) word = m[w];
-  return (word >> (b & 31)) & 1u;
+  for (int w = 0; w < W; w++) hit |= m[w] & bit_in_word(b, w);
+  return hit != 0u;
 }
 template <int W> __device__ __forceinline__ void bit_set(uint32_t (&m)[W], int b)
 {
+  if (W == 1) { m[0] |= 1u << (b & 31); return; }
 #pragma unroll
-  for (int w = 0; w < W; w++) if (W == 1 || (b >> 5) == w) m[w] |= 1u << (b & 31);
+  for (int w = 0; w < W; w++) m[w] |= bit_in_word(b, w);
 }
 template <int W> __device__ __forceinline__ void bit_clear(uint32_t (&m)[W], int b)
 {
+  if (W == 1) { m[0] &= ~(1u << (b & 31)); return; }
 #pragma unroll
-  for (int w = 0; w < W; w++) if (W == 1 || (b >> 5) == w) m[w] &= ~(1u << (b & 31));
+  for (int w = 0; w < W; w++) m[w] &= ~bit_in_word(b, w);
 }
 // mask of bit positions < x within one word (x may be <= 0 or >= 32).  PTX shl.b32 clamps shift amounts above 31
 // (the result is 0), so ~(~0 << max(x, 0)) is exact on the whole range without branches.
