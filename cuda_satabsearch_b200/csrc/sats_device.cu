@@ -423,7 +423,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
       for (int q = 0; q < Q; q++) {    // one launch per query, in order: the streams carry over
         const int n1 = s->q_n1[q];
         k.q_first = q;
-        k.sm_query_bytes = (int)s->q_bytes[q];
+        k.sm_query_bytes = words_for(n1) > 2 ? SATS_K_QUERY_HDR : (int)s->q_bytes[q];
         k.sm_mapwords = (n1 + 3) / 4;
         k.sm_team_bytes = (int)round16(k.sm_entry_bytes + (size_t)k.sm_mapwords * k.tw * 4 * (pp->lsoln ? 2 : 1) + 64);
         size_t smem = 16 + k.sm_query_bytes + k.sm_team_bytes;
@@ -447,7 +447,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
         int n1max = 0; uint32_t qbmax = 0;
         for (int q = q0; q < q1; q++) { n1max = std::max(n1max, s->q_n1[q]); qbmax = std::max(qbmax, s->q_bytes[q]); }
         k.q_first = q0;
-        k.sm_query_bytes = (int)qbmax;
+        k.sm_query_bytes = w1 > 2 ? SATS_K_QUERY_HDR : (int)qbmax;
         k.sm_mapwords = (n1max + 3) / 4;
         int b0 = r0;
         while (b0 < r1) {

@@ -322,7 +322,7 @@ struct Chain {
           while (bk) {
             int k = 32 * wk + __ffs(bk) - 1;
             bk &= bk - 1u;
-            total += gated(qrow[k], erow[map_get(v.smap, k, v.tw)]);
+            total += gated(W1 > 2 ? __ldg(qrow + k) : qrow[k], erow[map_get(v.smap, k, v.tw)]);
           }
         }
       }
@@ -336,7 +336,8 @@ struct Chain {
   {
     int d = 0;
     const int fmask = from >= 0 ? -1 : 0, tmask = to >= 0 ? -1 : 0;
-    uint32_t qrow = smem_u32(v.qcell) + (uint32_t)(i * v.n1) * 8u;                // row base addresses, hoisted by hand
+    const uint2 *qrow_g = v.qcell + i * v.n1;                                     // W1 == 4: query cells live in global memory
+    uint32_t qrow = W1 > 2 ? 0u : smem_u32(v.qcell) + (uint32_t)(i * v.n1) * 8u;  // row base addresses, hoisted by hand
     uint32_t frow = smem_u32(v.ecell) + (uint32_t)((from & fmask) * v.n2) * 8u;
     uint32_t trow = smem_u32(v.ecell) + (uint32_t)((to & tmask) * v.n2) * 8u;
     asm volatile("" : "+r"(qrow), "+r"(frow), "+r"(trow));       // keep the compiler from re-folding them into the loop
@@ -348,7 +349,7 @@ struct Chain {
         const int k = 32 * w + __ffs(b) - 1;
         b &= b - 1u;
         const int l = map_get(v.smap, k, v.tw);
-        const uint2 q = lds64(qrow + (uint32_t)k * 8u);
+        const uint2 q = W1 > 2 ? __ldg(qrow_g + k) : lds64(qrow + (uint32_t)k * 8u);
         const uint2 ef = lds64(frow + (uint32_t)l * 8u), et = lds64(trow + (uint32_t)l * 8u);
         d += (gated(q, et) & tmask) - (gated(q, ef) & fmask);
       }
@@ -506,7 +507,7 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
 
 // Shared-memory layout of a CTA:
 //   [0,16)                      mbarrier
-//   [16, 16 + sm_query_bytes)   query blob
+//   [16, 16 + sm_query_bytes)   query blob (header + SSE types only when W1 == 4)
 //   then per team: entry blob (sm_entry_bytes) | byte maps (mapwords*tw*4) | best maps (same, if lsoln) | 64 B reduce scratch
 #ifndef SATS_K_MAXTHREADS
 #define SATS_K_MAXTHREADS 384
@@ -535,7 +536,10 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
   v.tw = p.tw;
   v.mapwords = p.sm_mapwords;
   v.qtype = sq + 16;
-  v.qcell = reinterpret_cast<const uint2 *>(sq + SATS_K_QUERY_HDR);
+  // Queries of more than 64 SSEs (W1 == 4) keep their n1 x n1 cells in global memory (read through L1 with ld.global.nc):
+  // an 82 KB query copy per CTA would leave room for one CTA per SM.  Only header + SSE types are staged then.
+  v.qcell = W1 > 2 ? reinterpret_cast<const uint2 *>(p.qblobs + p.qblob_off[qi] + SATS_K_QUERY_HDR)
+                   : reinterpret_cast<const uint2 *>(sq + SATS_K_QUERY_HDR);
   v.tmask = reinterpret_cast<const uint32_t *>(se + 16);
   v.ecell = reinterpret_cast<const uint2 *>(se + SATS_K_ENTRY_HDR);
   v.smap = smaps + tl * 4;
@@ -547,10 +551,11 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
     const int first = p.item_first + blockIdx.x * p.teams;
     const int here = min(p.teams, p.item_first + p.item_count - first);
     if (threadIdx.x == 0) {
-      uint32_t total = p.qblob_bytes[qi];
+      const uint32_t qbytes = W1 > 2 ? (uint32_t)SATS_K_QUERY_HDR : p.qblob_bytes[qi];
+      uint32_t total = qbytes;
       for (int t = 0; t < here; t++) total += p.blob_bytes[first + t];
       mbar_expect_tx(bar, total);
-      tma_load_1d(sq, p.qblobs + p.qblob_off[qi], p.qblob_bytes[qi], bar);
+      tma_load_1d(sq, p.qblobs + p.qblob_off[qi], qbytes, bar);
       for (int t = 0; t < here; t++)
         tma_load_1d(smem + 16 + p.sm_query_bytes + (size_t)t * p.sm_team_bytes, p.blobs + p.blob_off[first + t],
                     p.blob_bytes[first + t], bar);
@@ -569,8 +574,9 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
     xw.load(st);
     uint32_t phase = 0;
     if (threadIdx.x == 0) {
-      mbar_expect_tx(bar, p.qblob_bytes[qi]);
-      tma_load_1d(sq, p.qblobs + p.qblob_off[qi], p.qblob_bytes[qi], bar);
+      const uint32_t qbytes = W1 > 2 ? (uint32_t)SATS_K_QUERY_HDR : p.qblob_bytes[qi];
+      mbar_expect_tx(bar, qbytes);
+      tma_load_1d(sq, p.qblobs + p.qblob_off[qi], qbytes, bar);
     }
     mbar_wait(bar, phase);
     phase ^= 1u;
