@@ -17,6 +17,8 @@
  *   -R mode   philox (default) | xorwow  -- xorwow = the reference GPU run's 128x128 cuRAND streams
  *   -A mode   table (default) | fast     -- Metropolis thresholds: host libm table | device fast-math
  *   -s seed   RNG seed (default 1234)
+ *   -k N      print only the N best-scoring structures of each (query, pool) block, best first (selected on the
+ *             device with sats_search_topk, so only N rows per query leave the GPU); single GPU, LSOLN = F
  */
 #include <getopt.h>
 #include <stdio.h>
@@ -43,7 +45,7 @@ static void die(const char *what)
 
 static void usage(const char *prog)
 {
-  fprintf(stderr, "Usage: %s [-c] [-q dbfile] [-r restarts] [-g gpus] [-R philox|xorwow] [-A table|fast] [-s seed]\n", prog);
+  fprintf(stderr, "Usage: %s [-c] [-q dbfile] [-r restarts] [-g gpus] [-R philox|xorwow] [-A table|fast] [-s seed] [-k tophits]\n", prog);
   fprintf(stderr, "  -c : (reference: run on host CPU) not available in this build\n");
   fprintf(stderr, "  -q dbfile : database is read from dbfile, list of query\n"
                   "              ids is read from stdin\n");
@@ -86,12 +88,12 @@ int main(int argc, char *argv[])
 {
   char dbfile[4096] = "";
   int querydbmode = 0, maxstart = SATS_DEFAULT_MAXSTART, ngpus = 1, c;
-  int rng_mode = SATS_RNG_PHILOX, accept_mode = SATS_ACCEPT_HOST_TABLE;
+  int rng_mode = SATS_RNG_PHILOX, accept_mode = SATS_ACCEPT_HOST_TABLE, topk = 0;
   unsigned long long seed = SATS_REF_SEED;
   int flags[3] = {1, 1, 0};
   sats_db *db = NULL, *queries = NULL;
 
-  while ((c = getopt(argc, argv, "cq:r:g:R:A:s:")) != -1) {
+  while ((c = getopt(argc, argv, "cq:r:g:R:A:s:k:")) != -1) {
     switch (c) {
       case 'c':
         fprintf(stderr, "ERROR: -c (host CPU search) is not available: this build is GPU-only\n");
@@ -110,6 +112,7 @@ int main(int argc, char *argv[])
         else usage(argv[0]);
         break;
       case 's': seed = strtoull(optarg, NULL, 0); break;
+      case 'k': topk = atoi(optarg); break;
       default: usage(argv[0]);
     }
   }
@@ -119,6 +122,7 @@ int main(int argc, char *argv[])
     fprintf(stderr, "ERROR: -R xorwow reproduces a single-GPU reference run; use -g 1\n");
     exit(1);
   }
+  if (topk < 0 || (topk > 0 && ngpus > 1)) { fprintf(stderr, "ERROR: -k needs a positive count and a single GPU\n"); exit(1); }
   fprintf(stderr, "MAXDIM = %d\n", SATS_MAXDIM);
 
   size_t inlen = 0;
@@ -148,6 +152,7 @@ int main(int argc, char *argv[])
     flags[0] = 1;
   }
   const int lorder = flags[1], lsoln = flags[2];
+  if (topk > 0 && lsoln) { fprintf(stderr, "ERROR: -k cannot be combined with LSOLN = T\n"); exit(1); }
 
   fprintf(stderr, "Loading database...\n");
   double t0 = now_ms();
@@ -214,12 +219,37 @@ int main(int argc, char *argv[])
         if (sats_search_upload(sr[g], queries, q0, nq) != SATS_OK) die("ERROR uploading queries");
       for (int g = 0; g < ngpus; g++)
         if (sats_search_launch(sr[g], &prm, (uint32_t)q0, NULL) != SATS_OK) die("kernel launch failed");
-      for (int g = 0; g < ngpus; g++)
-        if (sats_search_collect(sr[g], scores, maps) != SATS_OK) die("ERROR collecting results");
+      int32_t *top_idx = NULL, *top_sc = NULL;
+      if (topk > 0) {
+        top_idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)nq * (size_t)topk);
+        top_sc = (int32_t *)malloc(sizeof(int32_t) * (size_t)nq * (size_t)topk);
+        if (!top_idx || !top_sc) { fprintf(stderr, "malloc failed\n"); exit(1); }
+        if (sats_search_topk(sr[0], topk, top_idx, top_sc) != SATS_OK) die("ERROR selecting top hits");
+      } else {
+        for (int g = 0; g < ngpus; g++)
+          if (sats_search_collect(sr[g], scores, maps) != SATS_OK) die("ERROR collecting results");
+      }
       double ms = now_ms() - t1;
       fprintf(stderr, "GPU execution time %f ms (%d queries x %d entries, %s pool)\n", ms, nq, n, pass ? "large" : "small");
       fprintf(stderr, "%f million iterations/sec\n", ((double)nq * n * ((double)maxstart * SATS_MAXITER) / (ms / 1000)) / 1.0e6);
-      for (int q = 0; q < nq; q++) {
+      for (int q = 0; q < nq && topk > 0; q++) {
+        /* hits only: scatter the selected scores into this query's row and print them in rank order */
+        int32_t *sc = scores + (size_t)q * dbsize;
+        int nhit = 0;
+        while (nhit < topk && top_idx[(size_t)q * topk + nhit] >= 0) { sc[top_idx[(size_t)q * topk + nhit]] = top_sc[(size_t)q * topk + nhit]; nhit++; }
+        size_t need = sats_format_block(out, outcap, sats_db_name(queries, q0 + q), sats_db_order(queries, q0 + q), dbfile,
+                                        lorder, 0, db, top_idx + (size_t)q * topk, nhit, sc, NULL);
+        if (need >= outcap) {
+          outcap = need + 1;
+          out = (char *)realloc(out, outcap);
+          if (!out) { fprintf(stderr, "malloc failed\n"); exit(1); }
+          sats_format_block(out, outcap, sats_db_name(queries, q0 + q), sats_db_order(queries, q0 + q), dbfile, lorder, 0, db,
+                            top_idx + (size_t)q * topk, nhit, sc, NULL);
+        }
+        fwrite(out, 1, need, stdout);
+      }
+      free(top_idx); free(top_sc);
+      for (int q = 0; q < nq && topk == 0; q++) {
         const int32_t *sc = scores + (size_t)q * dbsize;
         const int32_t *mp = lsoln ? maps + (size_t)q * dbsize * SATS_MAP_STRIDE : NULL;
         size_t need = sats_format_block(out, outcap, sats_db_name(queries, q0 + q), sats_db_order(queries, q0 + q),

@@ -103,3 +103,23 @@ def test_cli_multi_gpu_output_is_identical(tmp_path, fixtures):
     two = run([CLI, "-r", 128, "-g", 2], tmp_path / "q.input", tmp_path)
     assert one.returncode == 0 and two.returncode == 0, two.stderr.decode()[-1000:]
     assert one.stdout == two.stdout and len(one.stdout) > 10000
+
+
+def test_cli_top_hits_only(tmp_path, fixtures):
+    """-k N prints the N best rows of each block (selected on the device), best first; the rows are the same rows
+    the full run prints."""
+    ents = fixtures["small586"]
+    q = fixtures["queries_by_name"]["D2PHLB1"]
+    write_ascii_db(tmp_path / "db.ascii", ents)
+    write_query_input(tmp_path / "q.input", "db.ascii", True, False, [q])
+    full = run([CLI, "-r", 128], tmp_path / "q.input", tmp_path)
+    top = run([CLI, "-r", 128, "-k", 25], tmp_path / "q.input", tmp_path)
+    assert full.returncode == 0 and top.returncode == 0, top.stderr.decode()[-1000:]
+    frows = [ln for ln in full.stdout.decode().split("\n") if ln and not ln.startswith("#")]
+    trows = [ln for ln in top.stdout.decode().split("\n") if ln and not ln.startswith("#")]
+    assert len(trows) == 25 and set(trows) <= set(frows)
+    tscores = [int(r.split()[1]) for r in trows]
+    assert tscores == sorted(tscores, reverse=True)
+    assert tscores[-1] >= sorted((int(r.split()[1]) for r in frows), reverse=True)[24]
+    blocks = S.parse_results(top.stdout)
+    assert len(blocks) == 1 and blocks[0]["query"] == "D2PHLB1" and len(blocks[0]["names"]) == 25
