@@ -28,7 +28,9 @@ struct sats_db {
 
 int sats_fail(int status, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
 
-// cost model used by the partitioner and by work ordering (recalibrated on device)
-static inline double sats_entry_cost(int order) { return 10.0 + 0.25 * (order < 40 ? order : 40); }
+// Cost model used by the partitioner (SURVEY 8e shape a + b*n2, recalibrated on a B200: per-entry kernel time by size
+// bucket in profiles/r01h_launches.txt is 0.107 us at order ~4 rising linearly to 0.43 us at order ~56, i.e.
+// proportional to 13 + order for the bench query; the shape is what matters for balancing).
+static inline double sats_entry_cost(int order) { return 13.0 + (double)order; }
 
 #endif

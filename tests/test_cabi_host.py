@@ -140,7 +140,7 @@ def test_partition_is_balanced_and_complete():
     for n in (1, 2, 3, 8):
         own = db.partition(n)
         assert own.min() == 0 and own.max() == n - 1
-        cost = 10.0 + 0.25 * np.minimum(orders, 40)
+        cost = 13.0 + orders
         loads = np.array([cost[own == r].sum() for r in range(n)])
         assert loads.max() - loads.min() <= cost.max() + 1e-9          # LPT bound
     big = db.bootstrap(20000, 20240501, True)
