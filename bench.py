@@ -145,16 +145,21 @@ def run_reference_gpu(S, db, count: int):
         qs.write_ascii(os.path.join(td, "q.ascii"))
         sample.write_ascii(os.path.join(td, "db.ascii"))
         Path(td, "in").write_text("db.ascii\nT T F\n" + Path(td, "q.ascii").read_text())
-        pr = subprocess.run([str(REF_BIN), "-r", str(RESTARTS)], stdin=open(os.path.join(td, "in")), stdout=subprocess.DEVNULL,
-                            stderr=subprocess.PIPE, cwd=td, text=True, timeout=600)
-    if pr.returncode != 0:
+        runs = []
+        for _ in range(3):            # a fresh process starts on an idle (down-clocked) GPU: keep the best of three
+            pr = subprocess.run([str(REF_BIN), "-r", str(RESTARTS)], stdin=open(os.path.join(td, "in")), stdout=subprocess.DEVNULL,
+                                stderr=subprocess.PIPE, cwd=td, text=True, timeout=600)
+            if pr.returncode != 0:
+                return None
+            ms = [float(x) for x in re.findall(r"GPU execution time ([0-9.]+) ms", pr.stderr)]
+            if ms:
+                runs.append(sum(ms))
+    if not runs:
         return None
-    ms = [float(x) for x in re.findall(r"GPU execution time ([0-9.]+) ms", pr.stderr)]
-    if not ms:
-        return None
-    return {"value": count / (sum(ms) / 1e3), "unit": "structures/s", "kernel_ms": sum(ms),
+    ms = [min(runs)]
+    return {"value": count / (sum(ms) / 1e3), "unit": "structures/s", "kernel_ms": sum(ms), "kernel_ms_all_runs": runs,
             "sample": "%d structures (size-stratified sample of the 100k synthetic db), the reference's sa_tabsearch_gpu<<<128,128>>> "
-                      "rebuilt with -arch=sm_100a and its own --use_fast_math, timed by its own 'GPU execution time'" % count}
+                      "rebuilt with -arch=sm_100a and its own --use_fast_math, timed by its own 'GPU execution time'; best of 3 runs" % count}
 
 
 def host_cores():
