@@ -18,6 +18,7 @@ LIB_PATH = _PKG / "libsats.so"
 CLI_PATH = _PKG / "bin" / "cudaSaTabsearch"
 
 MAXDIM = 111
+MAXDIM_EXT = 128
 MAP_STRIDE = 111
 RNG_PHILOX, RNG_XORWOW_GRID = 0, 1
 ACCEPT_HOST_TABLE, ACCEPT_DEVICE_FAST = 0, 1
@@ -44,6 +45,7 @@ def _load() -> C.CDLL:
     sig = {
         "sats_last_error": (cs, []), "sats_version": (cs, []),
         "sats_db_read_ascii": (ci, [cs, P(vp)]), "sats_db_parse_ascii": (ci, [cs, C.c_size_t, P(vp)]),
+        "sats_db_read_ascii_ext": (ci, [cs, ci, P(vp)]), "sats_db_parse_ascii_ext": (ci, [cs, C.c_size_t, ci, P(vp)]),
         "sats_input_parse": (ci, [cs, C.c_size_t, cs, C.c_size_t, P(ci), P(vp)]),
         "sats_idlist_parse": (ci, [cs, C.c_size_t, cs, ci]),
         "sats_db_from_arrays": (ci, [ci, vp, vp, vp, vp, vp, P(vp)]),
@@ -120,16 +122,16 @@ class Database:
 
     # -- constructors
     @classmethod
-    def read_ascii(cls, path):
+    def read_ascii(cls, path, max_order: int = MAXDIM):
         h = C.c_void_p()
-        _check(lib().sats_db_read_ascii(os.fsencode(path), C.byref(h)))
+        _check(lib().sats_db_read_ascii_ext(os.fsencode(path), max_order, C.byref(h)))
         return cls(h.value)
 
     @classmethod
-    def parse_ascii(cls, text: bytes | str):
+    def parse_ascii(cls, text: bytes | str, max_order: int = MAXDIM):
         b = text.encode() if isinstance(text, str) else text
         h = C.c_void_p()
-        _check(lib().sats_db_parse_ascii(b, len(b), C.byref(h)))
+        _check(lib().sats_db_parse_ascii_ext(b, len(b), max_order, C.byref(h)))
         return cls(h.value)
 
     @classmethod

@@ -17,6 +17,7 @@
  *   -R mode   philox (default) | xorwow  -- xorwow = the reference GPU run's 128x128 cuRAND streams
  *   -A mode   table (default) | fast     -- Metropolis thresholds: host libm table | device fast-math
  *   -s seed   RNG seed (default 1234)
+ *   -L        also search database structures of order 112..128 (the reference drops everything above 111)
  *   -k N      print only the N best-scoring structures of each (query, pool) block, best first (selected on the
  *             device with sats_search_topk, so only N rows per query leave the GPU); single GPU, LSOLN = F
  */
@@ -45,7 +46,7 @@ static void die(const char *what)
 
 static void usage(const char *prog)
 {
-  fprintf(stderr, "Usage: %s [-c] [-q dbfile] [-r restarts] [-g gpus] [-R philox|xorwow] [-A table|fast] [-s seed] [-k tophits]\n", prog);
+  fprintf(stderr, "Usage: %s [-c] [-q dbfile] [-r restarts] [-g gpus] [-R philox|xorwow] [-A table|fast] [-s seed] [-k tophits] [-L]\n", prog);
   fprintf(stderr, "  -c : (reference: run on host CPU) not available in this build\n");
   fprintf(stderr, "  -q dbfile : database is read from dbfile, list of query\n"
                   "              ids is read from stdin\n");
@@ -73,7 +74,7 @@ static char *read_all(FILE *fp, size_t *len)
   return buf;
 }
 
-static int load_db(const char *path, sats_db **db)
+static int load_db(const char *path, int max_order, sats_db **db)
 {
   FILE *fp = fopen(path, "rb");
   char magic[8] = {0};
@@ -81,19 +82,19 @@ static int load_db(const char *path, sats_db **db)
   size_t got = fread(magic, 1, 8, fp);
   fclose(fp);
   if (got == 8 && memcmp(magic, "SATSDB1", 8) == 0) return sats_db_read_packed(path, db);
-  return sats_db_read_ascii(path, db);
+  return sats_db_read_ascii_ext(path, max_order, db);
 }
 
 int main(int argc, char *argv[])
 {
   char dbfile[4096] = "";
   int querydbmode = 0, maxstart = SATS_DEFAULT_MAXSTART, ngpus = 1, c;
-  int rng_mode = SATS_RNG_PHILOX, accept_mode = SATS_ACCEPT_HOST_TABLE, topk = 0;
+  int rng_mode = SATS_RNG_PHILOX, accept_mode = SATS_ACCEPT_HOST_TABLE, topk = 0, max_order = SATS_MAXDIM;
   unsigned long long seed = SATS_REF_SEED;
   int flags[3] = {1, 1, 0};
   sats_db *db = NULL, *queries = NULL;
 
-  while ((c = getopt(argc, argv, "cq:r:g:R:A:s:k:")) != -1) {
+  while ((c = getopt(argc, argv, "cq:r:g:R:A:s:k:L")) != -1) {
     switch (c) {
       case 'c':
         fprintf(stderr, "ERROR: -c (host CPU search) is not available: this build is GPU-only\n");
@@ -113,6 +114,7 @@ int main(int argc, char *argv[])
         break;
       case 's': seed = strtoull(optarg, NULL, 0); break;
       case 'k': topk = atoi(optarg); break;
+      case 'L': max_order = SATS_MAXDIM_EXT; break;
       default: usage(argv[0]);
     }
   }
@@ -123,7 +125,7 @@ int main(int argc, char *argv[])
     exit(1);
   }
   if (topk < 0 || (topk > 0 && ngpus > 1)) { fprintf(stderr, "ERROR: -k needs a positive count and a single GPU\n"); exit(1); }
-  fprintf(stderr, "MAXDIM = %d\n", SATS_MAXDIM);
+  fprintf(stderr, "MAXDIM = %d\n", max_order);
 
   size_t inlen = 0;
   char *input = read_all(stdin, &inlen);
@@ -156,7 +158,7 @@ int main(int argc, char *argv[])
 
   fprintf(stderr, "Loading database...\n");
   double t0 = now_ms();
-  if (load_db(dbfile, &db) != SATS_OK) { fprintf(stderr, "%s\n", sats_last_error()); fprintf(stderr, "ERROR loading database\n"); exit(1); }
+  if (load_db(dbfile, max_order, &db) != SATS_OK) { fprintf(stderr, "%s\n", sats_last_error()); fprintf(stderr, "ERROR loading database\n"); exit(1); }
   const int dbsize = sats_db_count(db);
   int *small_idx = (int *)malloc(sizeof(int) * (size_t)(dbsize + 1));
   int *large_idx = (int *)malloc(sizeof(int) * (size_t)(dbsize + 1));

@@ -274,6 +274,7 @@ extern "C" int sats_search_upload(sats_searcher *s, const sats_db *queries, int 
   s->q_bytes.assign((size_t)qcount, 0);
   for (int q = 0; q < qcount; q++) {
     int n = queries->order[qfirst + q];
+    if (n > SATS_MAXDIM) return sats_fail(SATS_ERR_ARG, "query %s has order %d; queries are limited to %d SSEs", queries->name(qfirst + q), n, SATS_MAXDIM);
     s->q_n1[q] = n;
     off[q] = total;
     s->q_bytes[q] = (uint32_t)query_blob_bytes(n);
@@ -360,7 +361,7 @@ static int set_attrs_once(sats_searcher *s)
 }
 
 // upper bounds (entry order) of the launch buckets: each bucket is one launch with its own shared-memory sizing
-static const int kBucketBounds[] = {8, 12, 16, 20, 24, 32, 48, 64, 96, SATS_MAXDIM};
+static const int kBucketBounds[] = {8, 12, 16, 20, 24, 32, 48, 64, 96, SATS_MAXDIM, SATS_MAXDIM_EXT};
 
 extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint32_t query_index_base, float *elapsed_ms)
 {

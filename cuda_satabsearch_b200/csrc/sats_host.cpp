@@ -130,7 +130,7 @@ bool read_header(Cursor &c, char name[9], int *order)
 }
 
 // Parses consecutive entries until the text ends or a header fails to parse.
-int parse_entries(Cursor &c, const char *what, sats_db *db)
+int parse_entries(Cursor &c, const char *what, sats_db *db, int max_order = SATS_MAXDIM)
 {
   std::vector<uint8_t> ttab;
   std::vector<float> tdm;
@@ -139,9 +139,9 @@ int parse_entries(Cursor &c, const char *what, sats_db *db)
   int n;
   while (read_header(c, name, &n)) {
     if (n < 1) return sats_fail(SATS_ERR_PARSE, "%s structure %s has bad order %d", what, name, n);
-    bool keep = n <= SATS_MAXDIM;
+    bool keep = n <= max_order;
     if (!keep) {
-      fprintf(stderr, "Tableau %s order %d is too large (max is %d)\n", name, n, SATS_MAXDIM);
+      fprintf(stderr, "Tableau %s order %d is too large (max is %d)\n", name, n, max_order);
       fprintf(stderr, "WARNING: excluded %s structure %s as it is too large\n", what, name);
       skipped++;
     }
@@ -177,7 +177,7 @@ int parse_entries(Cursor &c, const char *what, sats_db *db)
     }
     if (keep) db->append(name, n, ttab.data(), tdm.data());
   }
-  if (skipped) fprintf(stderr, "WARNING: skipped %d %s tableaux of order > %d\n", skipped, what, SATS_MAXDIM);
+  if (skipped) fprintf(stderr, "WARNING: skipped %d %s tableaux of order > %d\n", skipped, what, max_order);
   return 0;
 }
 
@@ -194,26 +194,34 @@ int slurp(const char *path, std::string *out)
 
 }  // namespace
 
-extern "C" int sats_db_parse_ascii(const char *text, size_t len, sats_db **out)
+extern "C" int sats_db_parse_ascii_ext(const char *text, size_t len, int max_order, sats_db **out)
 {
   if (!text || !out) return sats_fail(SATS_ERR_ARG, "sats_db_parse_ascii: null argument");
+  if (max_order < 1 || max_order > SATS_MAXDIM_EXT) return sats_fail(SATS_ERR_ARG, "max_order %d outside 1..%d", max_order, SATS_MAXDIM_EXT);
   sats_db *db = new sats_db();
   db->tri_off.push_back(0);
   Cursor c{text, text + len};
-  int rc = parse_entries(c, "database", db);
+  int rc = parse_entries(c, "database", db, max_order);
   if (rc) { delete db; return rc; }
   *out = db;
   return SATS_OK;
 }
 
-extern "C" int sats_db_read_ascii(const char *path, sats_db **out)
+extern "C" int sats_db_parse_ascii(const char *text, size_t len, sats_db **out)
+{
+  return sats_db_parse_ascii_ext(text, len, SATS_MAXDIM, out);
+}
+
+extern "C" int sats_db_read_ascii_ext(const char *path, int max_order, sats_db **out)
 {
   if (!path || !out) return sats_fail(SATS_ERR_ARG, "sats_db_read_ascii: null argument");
   std::string text;
   int rc = slurp(path, &text);
   if (rc) return rc;
-  return sats_db_parse_ascii(text.data(), text.size(), out);
+  return sats_db_parse_ascii_ext(text.data(), text.size(), max_order, out);
 }
+
+extern "C" int sats_db_read_ascii(const char *path, sats_db **out) { return sats_db_read_ascii_ext(path, SATS_MAXDIM, out); }
 
 extern "C" int sats_input_parse(const char *text, size_t len, char *dbfile, size_t dbfile_cap, int flags_tf[3],
                                 sats_db **queries)
@@ -276,7 +284,7 @@ extern "C" int sats_db_from_arrays(int count, const int32_t *order, const char *
   std::vector<float> td;
   for (int e = 0; e < count; e++) {
     int n = order[e];
-    if (n < 1 || n > SATS_MAXDIM) { delete db; return sats_fail(SATS_ERR_ARG, "entry %d has order %d outside 1..%d", e, n, SATS_MAXDIM); }
+    if (n < 1 || n > SATS_MAXDIM_EXT) { delete db; return sats_fail(SATS_ERR_ARG, "entry %d has order %d outside 1..%d", e, n, SATS_MAXDIM_EXT); }
     tt.resize((size_t)n * (n + 1) / 2);
     td.resize(tt.size());
     const uint8_t *t = tabs + off[e];
@@ -445,7 +453,7 @@ extern "C" int sats_db_read_packed(const char *path, sats_db **out)
   uint64_t sum = 0;
   for (uint32_t e = 0; e < count; e++) {
     int n = db->order[e];
-    if (n < 1 || n > SATS_MAXDIM) { delete db; return sats_fail(SATS_ERR_PARSE, "%s: entry %u has order %d", path, e, n); }
+    if (n < 1 || n > SATS_MAXDIM_EXT) { delete db; return sats_fail(SATS_ERR_PARSE, "%s: entry %u has order %d", path, e, n); }
     sum += (uint64_t)n * (n + 1) / 2;
     db->tri_off.push_back((int64_t)sum);
   }

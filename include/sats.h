@@ -25,7 +25,8 @@ extern "C" {
 #endif
 
 /* ---- constants (saparams.h:15-46) ------------------------------------------------------------ */
-#define SATS_MAXDIM 111          /* MAXDIM: largest structure order the search handles             */
+#define SATS_MAXDIM 111          /* MAXDIM: largest structure order the reference handles          */
+#define SATS_MAXDIM_EXT 128      /* largest DATABASE structure order this library can search (opt-in)  */
 #define SATS_MAXDIM_GPU 96       /* MAXDIM_GPU: the reference's small/large pool split             */
 #define SATS_LABELSIZE 8         /* LABELSIZE: identifier length                                   */
 #define SATS_MAXITER 100         /* MAXITER: moves per restart                                     */
@@ -59,6 +60,11 @@ typedef struct sats_db sats_db;
 /* read_database(FILE*, ...) / read_queries(FILE*, ...): ASCII text from a file or from memory.   */
 int sats_db_read_ascii(const char *path, sats_db **out);
 int sats_db_parse_ascii(const char *text, size_t len, sats_db **out);
+/* the same, but keeping database structures of order up to max_order (<= SATS_MAXDIM_EXT = 128) instead of
+ * dropping everything above SATS_MAXDIM like the reference (parsetableaux.c:457-465).  Opt-in because it adds rows to
+ * the output; queries stay limited to SATS_MAXDIM (the SSE-map row stride).                                         */
+int sats_db_read_ascii_ext(const char *path, int max_order, sats_db **out);
+int sats_db_parse_ascii_ext(const char *text, size_t len, int max_order, sats_db **out);
 /* The reference's stdin grammar in non -q mode (cudaSaTabsearch.cu:667-693): line 1 db path,
  * line 2 "LTYPE LORDER LSOLN" as T/F, then query structures.  flags_tf[3] receives 0/1.         */
 int sats_input_parse(const char *text, size_t len, char *dbfile, size_t dbfile_cap, int flags_tf[3],

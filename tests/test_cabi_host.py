@@ -90,6 +90,11 @@ def test_parser_edge_cases():
     big = "BIG      %4d\n" % n + "".join("PE " * i + "e  \n" for i in range(n)) + "".join(" 1.000 " * (i + 1) + "\n" for i in range(n))
     db = S.Database.parse_ascii(big + "\n" + one)
     assert len(db) == 1 and db.name(0) == "A"
+    # SURVEY 8(f4), opt-in: the same text with max_order=128 keeps the big structure (and 129 is refused)
+    db = S.Database.parse_ascii(big + "\n" + one, max_order=S.MAXDIM_EXT)
+    assert len(db) == 2 and db.name(0) == "BIG" and db.order(0) == 112 and db.get(0)[1][111, 0] == np.float32(1.0)
+    with pytest.raises(S.SatsError, match="max_order"):
+        S.Database.parse_ascii(one, max_order=S.MAXDIM_EXT + 1)
     # the 5x5 code alphabet incl. '?' (parsetableaux.c:92-138)
     q = "C          2\nxg \n?? xi \n 3.000 \n 9.999  2.000 \n"
     t, d = S.Database.parse_ascii(q).get(0)

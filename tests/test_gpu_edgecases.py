@@ -93,3 +93,33 @@ def test_empty_database_and_empty_pool(synth):
     sr.search(to_db(queries[:1]), S.default_params(restarts=32, pool=S.POOL_LARGE), scores=sc)
     assert (sc == -7).all()                                   # nothing in the large pool: outputs untouched
     sr.close()
+
+
+@pytest.mark.parametrize("lorder,lsoln,restarts", [(True, True, 128), (False, True, 40), (True, False, 96)])
+def test_database_orders_above_111(synth, oracle, lorder, lsoln, restarts, tmp_path):
+    """database structures of order 112..128 (the reference drops them, parsetableaux.c:457-465) are
+    searched when the caller opts in; results still equal the oracle's, whose working arrays hold 128 SSEs."""
+    _, queries = synth
+    rng = np.random.default_rng(777)
+    ents = [random_structure(rng, "L%05d" % k, n) for k, n in enumerate([112, 113, 120, 127, 128, 128, 30, 96, 111, 5])]
+    qs = [queries[3], queries[5], queries[7]]                 # n1 = 19, 33, 111
+    sr = S.Searcher(to_db(ents), 0)
+    p = S.default_params(lorder=lorder, lsoln=lsoln, restarts=restarts, seed=99)
+    got_s, got_m = sr.search(to_db(qs), p)
+    for k, q in enumerate(qs):
+        want_s, want_m = oracle.search_philox(q, ents, lorder=lorder, lsoln=lsoln, restarts=restarts, seed=99, query_index=k)
+        assert np.array_equal(got_s[k], want_s), (k, q.n, got_s[k], want_s)
+        if lsoln:
+            assert np.array_equal(got_m[k, :, :q.n], want_m[:, :q.n]), (k, q.n)
+    sr.close()
+    # a query of more than 111 SSEs is refused (the SSE-map row stride is the reference's MAXDIM)
+    sr = S.Searcher(to_db(ents[:2]), 0)
+    with pytest.raises(S.SatsError, match="limited to 111"):
+        sr.search(to_db([ents[0]]), S.default_params(restarts=32))
+    sr.close()
+    # the ASCII route: default reader drops them, the opt-in reader keeps them
+    from _refio import write_ascii_db
+    small_d = [Structure(s.name, s.tab, np.nan_to_num(np.minimum(s.dmat, np.float32(99.999)))) for s in ents]
+    write_ascii_db(tmp_path / "big.ascii", small_d)
+    assert len(S.Database.read_ascii(tmp_path / "big.ascii")) == 4
+    assert len(S.Database.read_ascii(tmp_path / "big.ascii", max_order=S.MAXDIM_EXT)) == 10
