@@ -421,13 +421,14 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
       k.pool_count = (int)list.size();
       k.tw = SATS_REF_GRID_THREADS; k.teams = 1;
       k.sm_entry_bytes = (int)entry_blob_bytes(n2max);
+      k.sm_nan_bytes = (int)round16(8 * (size_t)n2max);
       for (int q = 0; q < Q; q++) {    // one launch per query, in order: the streams carry over
         const int n1 = s->q_n1[q];
         k.q_first = q;
         k.sm_query_bytes = words_for(n1) > 2 ? SATS_K_QUERY_HDR : (int)s->q_bytes[q];
-        k.sm_mapwords = (n1 + 3) / 4;
+        k.sm_mapwords = n1;
         k.sm_team_bytes = (int)round16(k.sm_entry_bytes + (size_t)k.sm_mapwords * k.tw * 4 * (pp->lsoln ? 2 : 1) + 64);
-        size_t smem = 16 + k.sm_query_bytes + k.sm_team_bytes;
+        size_t smem = 16 + k.sm_query_bytes + k.sm_nan_bytes + k.sm_team_bytes;
         if (smem > (size_t)kMaxSmem) return sats_fail(SATS_ERR_ARG, "query %d x entry order %d needs %zu B of shared memory", q, n2max, smem);
         kernel_fn fn = pick_kernel(words_for(n1), words_for(n2max), pp->lorder != 0, true);
         fn<<<dim3((unsigned)blocks.size(), 1), k.tw, smem, s->stream>>>(k);
@@ -435,8 +436,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
         s->launches++;
       }
     } else {
-      const int tw = std::min(128, ((pp->restarts + 31) / 32) * 32);
-      k.tw = tw;
+      const int tw_max = std::min(128, ((pp->restarts + 31) / 32) * 32);
       CK(cudaEventRecord(s->fork, s->stream));
       for (int i = 0; i < sats_searcher::kSide; i++) CK(cudaStreamWaitEvent(s->side[i], s->fork, 0));
       int nlaunch = 0;
@@ -449,7 +449,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
         for (int q = q0; q < q1; q++) { n1max = std::max(n1max, s->q_n1[q]); qbmax = std::max(qbmax, s->q_bytes[q]); }
         k.q_first = q0;
         k.sm_query_bytes = w1 > 2 ? SATS_K_QUERY_HDR : (int)qbmax;
-        k.sm_mapwords = (n1max + 3) / 4;
+        k.sm_mapwords = n1max;
         int b0 = r0;
         while (b0 < r1) {
           // bucket = maximal run of entries whose order falls under the same bound (list is decreasing)
@@ -459,22 +459,30 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
           int b1 = b0;
           while (b1 < r1 && s->sorted_order[b1] > lowbound) b1++;
           k.sm_entry_bytes = (int)entry_blob_bytes(n2max);
-          k.sm_team_bytes = (int)round16(k.sm_entry_bytes + (size_t)k.sm_mapwords * tw * 4 * (pp->lsoln ? 2 : 1) + 64);
+          k.sm_nan_bytes = (int)round16(8 * (size_t)n2max);
           kernel_fn fn = pick_kernel(w1, words_for(n2max), pp->lorder != 0, false);
-          // teams per CTA: as many as fit while keeping the most warps resident per SM
-          int best_teams = 0, best_warps = -1;
-          for (int teams = SATS_K_MAXTHREADS / tw; teams >= 1; teams--) {
-            size_t smem = 16 + k.sm_query_bytes + (size_t)teams * k.sm_team_bytes;
-            if (smem > (size_t)kMaxSmem) continue;
-            int ctas = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, fn, teams * tw, smem));
-            int warps = ctas * teams * tw / 32;
-            if (warps > best_warps) { best_warps = warps; best_teams = teams; }
+          // team width (threads sharing one entry; results do not depend on it) and teams per CTA: whatever keeps the
+          // most warps resident per SM; a narrower team only when it buys strictly more
+          int best_teams = 0, best_warps = -1, best_tw = 0, best_team_bytes = 0;
+          for (int tw = tw_max; tw >= 32; tw >>= 1) {
+            if (tw & 31) continue;             // 96 -> 48: not a whole number of warps
+            const int team_bytes = (int)round16(k.sm_entry_bytes + (size_t)k.sm_mapwords * tw * 4 * (pp->lsoln ? 2 : 1) + 64);
+            for (int teams = SATS_K_MAXTHREADS / tw; teams >= 1; teams--) {
+              size_t smem = 16 + k.sm_query_bytes + k.sm_nan_bytes + (size_t)teams * team_bytes;
+              if (smem > (size_t)kMaxSmem) continue;
+              int ctas = 0;
+              CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, fn, teams * tw, smem));
+              int warps = ctas * teams * tw / 32;
+              if (warps > best_warps) { best_warps = warps; best_teams = teams; best_tw = tw; best_team_bytes = team_bytes; }
+            }
           }
           if (best_teams == 0) return sats_fail(SATS_ERR_ARG, "query order %d x entry order %d does not fit in shared memory", n1max, n2max);
+          const int tw = best_tw;
+          k.tw = tw;
           k.teams = best_teams;
+          k.sm_team_bytes = best_team_bytes;
           k.item_first = b0; k.item_count = b1 - b0;
-          size_t smem = 16 + k.sm_query_bytes + (size_t)k.teams * k.sm_team_bytes;
+          size_t smem = 16 + k.sm_query_bytes + k.sm_nan_bytes + (size_t)k.teams * k.sm_team_bytes;
           dim3 grid((unsigned)((k.item_count + k.teams - 1) / k.teams), (unsigned)(q1 - q0));
           fn<<<grid, k.teams * tw, smem, s->side[nlaunch % sats_searcher::kSide]>>>(k);
           CK(cudaGetLastError());

@@ -9,8 +9,9 @@
 //     copy of the query.  Teams synchronise with named barriers only.
 //   * The query blob and every team's entry blob are brought into shared memory by TMA 1-D bulk copies
 //     (cp.async.bulk ... mbarrier::complete_tx) issued by one thread; everybody waits on the mbarrier.
-//   * Chain state is bit masks in registers (mapped query SSEs, occupied entry SSEs) plus a byte map in
-//     lane-private, bank-conflict-free shared memory.  The LORDER window and the candidate list of the
+//   * Chain state is bit masks in registers (mapped query SSEs, occupied entry SSEs) plus a map of one 32-bit word
+//     per query SSE (the partner's index pre-multiplied by the 8-byte cell size) in lane-private, bank-conflict-free
+//     shared memory.  The LORDER window and the candidate list of the
 //     reference (linear scans, kernel.cu:1053-1083, :677-714) become O(1) mask arithmetic: clz/ffs for the
 //     neighbouring mapped SSEs, (type mask & ~occupied & range mask) for the candidates, popc/select-nth
 //     for the random pick.  deltasd walks only the *mapped* SSEs (set bits), reading one 8-byte
@@ -57,7 +58,8 @@ struct SatsKParams {
   int teams;                       // teams per CTA
   int sm_query_bytes;              // room for the largest query blob of this launch
   int sm_entry_bytes;              // room for the largest entry blob of this launch
-  int sm_mapwords;                 // 32-bit words per chain byte-map (ceil(n1max / 4))
+  int sm_nan_bytes;                // room for one row of NaN-distance cells (8 B x largest entry order of this launch)
+  int sm_mapwords;                 // 32-bit words per chain map (n1max: one word per query SSE)
   int sm_team_bytes;               // total per team
   // search parameters
   int restarts, lsoln, accept_mode;
@@ -140,6 +142,21 @@ __device__ __forceinline__ uint32_t below(int x)
   uint32_t r;
   asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(0xffffffffu), "r"((uint32_t)max(x, 0)));
   return ~r;
+}
+
+// index of the highest set bit (x != 0): one FLO
+__device__ __forceinline__ int top_bit(uint32_t x)
+{
+  int r;
+  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
+// mask of bit positions < n, 0 <= n <= 31: one BMSK
+__device__ __forceinline__ uint32_t bits_below(int n)
+{
+  uint32_t r;
+  asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(r) : "r"(0), "r"(n));
+  return r;
 }
 
 // highest set bit with index <= i, or -1
@@ -244,29 +261,29 @@ __device__ __forceinline__ int gated(uint2 q, uint2 e)
   return gap <= 4.0f ? zeta(q.y, e.y) : 0;
 }
 
-// Per-team view of shared memory
+// Per-team view of shared memory (shared-window byte addresses)
 struct TeamView {
-  const uint2 *qcell;      // n1 x n1 {distance bits, code}
+  const uint2 *qcell_g;    // W1 == 4 only: the query's n1 x n1 cells in global memory
+  uint32_t qcell;          // n1 x n1 {distance bits, code} (W1 <= 2)
   const uint8_t *qtype;    // n1
-  const uint2 *ecell;      // n2 x n2
+  uint32_t ecell;          // n2 x n2
+  uint32_t nanrow;         // one row of cells whose distance is NaN: stands in for the missing side of a move
   const uint32_t *tmask;   // [4][4] type -> 128-bit mask of entry SSEs of that type
-  uint8_t *smap;           // this lane's byte map: byte k at smap[((k >> 2) * tw) * 4 + (k & 3)]
-  uint8_t *bmap;           // best map, same addressing
-  int n1, n2, tw, mapwords;
+  uint32_t smap;           // this lane's map: word k at smap + k * mstride holds 8 * partner (or -8 = unmapped)
+  uint32_t bmap;           // best map, same addressing
+  uint32_t mstride;        // tw * 4: consecutive lanes own consecutive banks, so lane-private accesses never conflict
+  int n1, n2, tw;
 };
 
-// byte k of a lane-private map: word k/4 of this lane is tw words after word k/4 - 1; the lane's slot is 4-byte aligned,
-// so the byte-in-word can be OR-ed into the base (one LOP3) and the word stride applied with one IMAD
-__device__ __forceinline__ uint32_t map_addr(uint32_t base, int k, int tw) { return (uint32_t)(k >> 2) * (uint32_t)(tw << 2) + (base | (uint32_t)(k & 3)); }
-__device__ __forceinline__ uint8_t map_get(const uint8_t *m, int k, int tw)
+__device__ __forceinline__ int map_get(uint32_t base, int k, uint32_t stride)
 {
-  uint32_t v;
-  asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(map_addr(smem_u32(m), k, tw)) : "memory");
-  return (uint8_t)v;
+  int v;
+  asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)k * stride) : "memory");
+  return v;
 }
-__device__ __forceinline__ void map_put(uint8_t *m, int k, int tw, uint8_t v)
+__device__ __forceinline__ void map_put(uint32_t base, int k, uint32_t stride, int v)
 {
-  asm volatile("st.shared.u8 [%0], %1;" ::"r"(map_addr(smem_u32(m), k, tw)), "r"((uint32_t)v) : "memory");
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (uint32_t)k * stride), "r"(v) : "memory");
 }
 
 template <int W1, int W2, bool LORDER, bool XORWOW>
@@ -282,7 +299,7 @@ struct Chain {
     for (int w = 0; w < W1; w++) mq[w] = 0u;
 #pragma unroll
     for (int w = 0; w < W2; w++) md[w] = 0u;
-    for (int w = 0; w < v.mapwords; w++) reinterpret_cast<uint32_t *>(v.smap)[w * v.tw] = 0xffffffffu;
+    for (int k = 0; k < v.n1; k++) map_put(v.smap, k, v.mstride, -8);
     int next_j = 0;
     for (int i = 0; i < v.n1; i++) {
       float u = draw(i);
@@ -293,7 +310,7 @@ struct Chain {
         for (int w = 0; w < W2; w++) cand[w] = tm[w];
         int j = low_at_or_above<W2>(cand, next_j);
         if (j < 0) break;
-        map_put(v.smap, i, v.tw, (uint8_t)j);
+        map_put(v.smap, i, v.mstride, j * 8);
         bit_set<W1>(mq, i);
         bit_set<W2>(md, j);
         next_j = j + 1;
@@ -311,9 +328,9 @@ struct Chain {
       while (bi) {
         int i = 32 * wi + __ffs(bi) - 1;
         bi &= bi - 1u;
-        int j = map_get(v.smap, i, v.tw);
-        const uint2 *qrow = v.qcell + i * v.n1;
-        const uint2 *erow = v.ecell + j * v.n2;
+        const uint32_t erow = v.ecell + (uint32_t)(map_get(v.smap, i, v.mstride) * v.n2);
+        const uint32_t qrow = v.qcell + (uint32_t)(i * v.n1) * 8u;
+        const uint2 *qrow_g = v.qcell_g + i * v.n1;
 #pragma unroll
         for (int wk = 0; wk < W1; wk++) {
           if (wk < wi) continue;
@@ -322,7 +339,8 @@ struct Chain {
           while (bk) {
             int k = 32 * wk + __ffs(bk) - 1;
             bk &= bk - 1u;
-            total += gated(W1 > 2 ? __ldg(qrow + k) : qrow[k], erow[map_get(v.smap, k, v.tw)]);
+            total += gated(W1 > 2 ? __ldg(qrow_g + k) : lds64(qrow + (uint32_t)k * 8u),
+                           lds64(erow + (uint32_t)map_get(v.smap, k, v.mstride)));
           }
         }
       }
@@ -330,28 +348,29 @@ struct Chain {
     return total;
   }
 
-  // deltasd (kernel.cu:502-535) over mapped SSEs only.  Branch-free body: a missing `from` / `to` side reads row 0 and is
-  // masked out, so lanes with one-sided and two-sided moves run the same instructions.
+  // deltasd (kernel.cu:502-535) over mapped SSEs only.  Branch-free body: a missing `from` / `to` side reads the row
+  // of NaN distances, whose gate never opens, so lanes with one-sided and two-sided moves run the same instructions.
+  // The mapped SSEs are walked from the top bit down (one FLO + one BMSK per term; the sum does not care about order).
   __device__ __forceinline__ int delta(const TeamView &v, int i, int from, int to) const
   {
     int d = 0;
-    const int fmask = from >= 0 ? -1 : 0, tmask = to >= 0 ? -1 : 0;
-    const uint2 *qrow_g = v.qcell + i * v.n1;                                     // W1 == 4: query cells live in global memory
-    uint32_t qrow = W1 > 2 ? 0u : smem_u32(v.qcell) + (uint32_t)(i * v.n1) * 8u;  // row base addresses, hoisted by hand
-    uint32_t frow = smem_u32(v.ecell) + (uint32_t)((from & fmask) * v.n2) * 8u;
-    uint32_t trow = smem_u32(v.ecell) + (uint32_t)((to & tmask) * v.n2) * 8u;
+    const uint2 *qrow_g = v.qcell_g + i * v.n1;                         // W1 == 4: query cells live in global memory
+    uint32_t qrow = W1 > 2 ? 0u : v.qcell + (uint32_t)(i * v.n1) * 8u;  // row base addresses, hoisted by hand
+    uint32_t frow = from >= 0 ? v.ecell + (uint32_t)(from * v.n2) * 8u : v.nanrow;
+    uint32_t trow = to >= 0 ? v.ecell + (uint32_t)(to * v.n2) * 8u : v.nanrow;
     asm volatile("" : "+r"(qrow), "+r"(frow), "+r"(trow));       // keep the compiler from re-folding them into the loop
 #pragma unroll
     for (int w = 0; w < W1; w++) {
       uint32_t b = mq[w];
       if (W1 == 1 || (i >> 5) == w) b &= ~(1u << (i & 31));
       while (b) {
-        const int k = 32 * w + __ffs(b) - 1;
-        b &= b - 1u;
-        const int l = map_get(v.smap, k, v.tw);
+        const int z = top_bit(b);
+        b &= bits_below(z);
+        const int k = 32 * w + z;
+        const uint32_t l8 = (uint32_t)map_get(v.smap, k, v.mstride);
         const uint2 q = W1 > 2 ? __ldg(qrow_g + k) : lds64(qrow + (uint32_t)k * 8u);
-        const uint2 ef = lds64(frow + (uint32_t)l * 8u), et = lds64(trow + (uint32_t)l * 8u);
-        d += (gated(q, et) & tmask) - (gated(q, ef) & fmask);
+        const uint2 ef = lds64(frow + l8), et = lds64(trow + l8);
+        d += gated(q, et) - gated(q, ef);
       }
     }
     return d;
@@ -368,16 +387,16 @@ struct Chain {
     int lo, hi, from;
     if (LORDER) {
       int kp = top_at_or_below<W1>(mq, i);
-      lo = kp >= 0 ? (int)map_get(v.smap, kp, v.tw) : v.n2;
+      lo = kp >= 0 ? map_get(v.smap, kp, v.mstride) >> 3 : v.n2;
       from = was_mapped ? lo : -1;
       if (i == v.n1 - 1) hi = v.n2;
       else {
         int kn = low_at_or_above<W1>(mq, i + 1);
-        hi = kn >= 0 ? (int)map_get(v.smap, kn, v.tw) : -1;
+        hi = kn >= 0 ? map_get(v.smap, kn, v.mstride) >> 3 : -1;
       }
     } else {
       lo = 0; hi = v.n2;
-      from = was_mapped ? (int)map_get(v.smap, i, v.tw) : -1;
+      from = was_mapped ? map_get(v.smap, i, v.mstride) >> 3 : -1;
     }
     // randtypeind (kernel.cu:677-714): unoccupied entry SSEs of the right type inside [lo, hi)
     const uint32_t *tm = v.tmask + 4 * v.qtype[i];
@@ -399,9 +418,8 @@ struct Chain {
       best = cand_score;
       best_tag = tag;
       if (p.lsoln) {
-        for (int w = 0; w < v.mapwords; w++)
-          reinterpret_cast<uint32_t *>(v.bmap)[w * v.tw] = reinterpret_cast<const uint32_t *>(v.smap)[w * v.tw];
-        map_put(v.bmap, i, v.tw, (uint8_t)to);     // -1 -> 0xff
+        for (int k = 0; k < v.n1; k++) map_put(v.bmap, k, v.mstride, map_get(v.smap, k, v.mstride));
+        map_put(v.bmap, i, v.mstride, to * 8);     // -1 -> -8
       }
     }
     const float u = u3();
@@ -421,7 +439,7 @@ struct Chain {
       if (from >= 0) bit_clear<W2>(md, from);
       if (to >= 0) { bit_set<W2>(md, to); bit_set<W1>(mq, i); }
       else bit_clear<W1>(mq, i);
-      if (from >= 0 || to >= 0) map_put(v.smap, i, v.tw, (uint8_t)to);
+      if (from >= 0 || to >= 0) map_put(v.smap, i, v.mstride, to * 8);
     }
   }
 };
@@ -461,8 +479,7 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
       best = ch.score;
       best_tag = tag;
       if (p.lsoln)
-        for (int w = 0; w < v.mapwords; w++)
-          reinterpret_cast<uint32_t *>(v.bmap)[w * v.tw] = reinterpret_cast<const uint32_t *>(v.smap)[w * v.tw];
+        for (int k = 0; k < v.n1; k++) map_put(v.bmap, k, v.mstride, map_get(v.smap, k, v.mstride));
     }
     if (XORWOW) {
       for (int m = 0; m < SATS_K_MOVES; m++)
@@ -497,8 +514,7 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
   if (tl == 0) p.out_scores[(size_t)out_slot * p.out_stride + entry_sorted] = team_best;
   if (p.lsoln && best == team_best && (unsigned)best_tag == team_tag) {
     int8_t *row = p.out_maps + ((size_t)out_slot * p.out_stride + entry_sorted) * SATS_K_MAPROW;
-    for (int w = 0; w < v.mapwords; w++)
-      reinterpret_cast<uint32_t *>(row)[w] = reinterpret_cast<const uint32_t *>(v.bmap)[w * v.tw];
+    for (int k = 0; k < v.n1; k++) row[k] = (int8_t)(map_get(v.bmap, k, v.mstride) >> 3);    // -8 -> -1 = unmapped
   }
   team_sync(team, p.tw);     // red[] and the entry buffer may be reused after this
 }
@@ -508,7 +524,8 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
 // Shared-memory layout of a CTA:
 //   [0,16)                      mbarrier
 //   [16, 16 + sm_query_bytes)   query blob (header + SSE types only when W1 == 4)
-//   then per team: entry blob (sm_entry_bytes) | byte maps (mapwords*tw*4) | best maps (same, if lsoln) | 64 B reduce scratch
+//   then sm_nan_bytes           one row of {NaN, 0} cells
+//   then per team: entry blob (sm_entry_bytes) | maps (mapwords*tw*4) | best maps (same, if lsoln) | 64 B reduce scratch
 #ifndef SATS_K_MAXTHREADS
 #define SATS_K_MAXTHREADS 384
 #define SATS_K_MINBLOCKS 3
@@ -520,8 +537,9 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
   uint8_t *sq = smem + 16;
+  uint2 *snan = reinterpret_cast<uint2 *>(sq + p.sm_query_bytes);
   const int team = threadIdx.x / p.tw, tl = threadIdx.x - team * p.tw;
-  uint8_t *steam = smem + 16 + p.sm_query_bytes + (size_t)team * p.sm_team_bytes;
+  uint8_t *steam = smem + 16 + p.sm_query_bytes + p.sm_nan_bytes + (size_t)team * p.sm_team_bytes;
   uint8_t *se = steam;
   uint8_t *smaps = se + p.sm_entry_bytes;
   const int mapbytes = p.sm_mapwords * p.tw * 4;
@@ -530,20 +548,22 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
 
   const int qi = p.q_first + blockIdx.y;     // query slot of this batch: selects the blob and the output row
   if (threadIdx.x == 0) mbar_init(bar, 1);
+  for (int c = threadIdx.x; c < (p.sm_nan_bytes >> 3); c += blockDim.x) snan[c] = make_uint2(0x7fc00000u, 0u);
   __syncthreads();
 
   TeamView v;
   v.tw = p.tw;
-  v.mapwords = p.sm_mapwords;
+  v.mstride = (uint32_t)p.tw * 4u;
   v.qtype = sq + 16;
   // Queries of more than 64 SSEs (W1 == 4) keep their n1 x n1 cells in global memory (read through L1 with ld.global.nc):
   // an 82 KB query copy per CTA would leave room for one CTA per SM.  Only header + SSE types are staged then.
-  v.qcell = W1 > 2 ? reinterpret_cast<const uint2 *>(p.qblobs + p.qblob_off[qi] + SATS_K_QUERY_HDR)
-                   : reinterpret_cast<const uint2 *>(sq + SATS_K_QUERY_HDR);
+  v.qcell_g = reinterpret_cast<const uint2 *>(p.qblobs + p.qblob_off[qi] + SATS_K_QUERY_HDR);
+  v.qcell = smem_u32(sq + SATS_K_QUERY_HDR);
+  v.nanrow = smem_u32(snan);
   v.tmask = reinterpret_cast<const uint32_t *>(se + 16);
-  v.ecell = reinterpret_cast<const uint2 *>(se + SATS_K_ENTRY_HDR);
-  v.smap = smaps + tl * 4;
-  v.bmap = bmaps + tl * 4;
+  v.ecell = smem_u32(se + SATS_K_ENTRY_HDR);
+  v.smap = smem_u32(smaps + tl * 4);
+  v.bmap = smem_u32(bmaps + tl * 4);
   Xorwow xw;
 
   if (!XORWOW) {
@@ -557,7 +577,7 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
       mbar_expect_tx(bar, total);
       tma_load_1d(sq, p.qblobs + p.qblob_off[qi], qbytes, bar);
       for (int t = 0; t < here; t++)
-        tma_load_1d(smem + 16 + p.sm_query_bytes + (size_t)t * p.sm_team_bytes, p.blobs + p.blob_off[first + t],
+        tma_load_1d(smem + 16 + p.sm_query_bytes + p.sm_nan_bytes + (size_t)t * p.sm_team_bytes, p.blobs + p.blob_off[first + t],
                     p.blob_bytes[first + t], bar);
     }
     mbar_wait(bar, 0);
