@@ -14,7 +14,7 @@
 #include <curand_kernel.h>
 
 #include "sats_internal.h"
-#include "sats_kernel.cuh"
+#include "sats_kparams.h"
 
 #define CK(call)                                                                                         \
   do {                                                                                                   \
@@ -78,24 +78,13 @@ struct sats_searcher {
   bool attr_done = false;
 };
 
-typedef void (*kernel_fn)(const SatsKParams);
-template <int W1, int W2> static kernel_fn pick2(bool lorder, bool xorwow)
+typedef sats_kernel_fn kernel_fn;
+static kernel_fn pick_kernel(int w1, int w2, bool lorder, bool xorwow, bool lsoln)
 {
-  if (xorwow) return lorder ? sats_anneal_kernel<W1, W2, true, true> : sats_anneal_kernel<W1, W2, false, true>;
-  return lorder ? sats_anneal_kernel<W1, W2, true, false> : sats_anneal_kernel<W1, W2, false, false>;
-}
-static kernel_fn pick_kernel(int w1, int w2, bool lorder, bool xorwow)
-{
-  switch (w1 * 8 + w2) {
-    case 1 * 8 + 1: return pick2<1, 1>(lorder, xorwow);
-    case 1 * 8 + 2: return pick2<1, 2>(lorder, xorwow);
-    case 1 * 8 + 4: return pick2<1, 4>(lorder, xorwow);
-    case 2 * 8 + 1: return pick2<2, 1>(lorder, xorwow);
-    case 2 * 8 + 2: return pick2<2, 2>(lorder, xorwow);
-    case 2 * 8 + 4: return pick2<2, 4>(lorder, xorwow);
-    case 4 * 8 + 1: return pick2<4, 1>(lorder, xorwow);
-    case 4 * 8 + 2: return pick2<4, 2>(lorder, xorwow);
-    default: return pick2<4, 4>(lorder, xorwow);
+  switch (w1) {
+    case 1: return sats_pick_kernel_w1(w2, lorder, xorwow, lsoln);
+    case 2: return sats_pick_kernel_w2(w2, lorder, xorwow, lsoln);
+    default: return sats_pick_kernel_w4(w2, lorder, xorwow, lsoln);
   }
 }
 static int words_for(int n) { return n <= 32 ? 1 : (n <= 64 ? 2 : 4); }
@@ -199,9 +188,9 @@ extern "C" int sats_searcher_create(const sats_db *db, int device, int shard_ran
     for (int d = 0; d <= SATS_K_DCLAMP; d++) tab[(size_t)m * (SATS_K_DCLAMP + 1) + d] = expf((float)(-d) / t);
     t *= 0.95f;
   }
-  CKF(cudaMalloc(&s->d_accept, tab.size() * 4));
+  CKF(cudaMalloc(&s->d_accept, (tab.size() + temps.size()) * 4));      // thresholds, then the temperature schedule
   CKF(cudaMemcpy(s->d_accept, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
-  CKF(cudaMemcpyToSymbol(c_sats_temps, temps.data(), temps.size() * 4));
+  CKF(cudaMemcpy(s->d_accept + tab.size(), temps.data(), temps.size() * 4, cudaMemcpyHostToDevice));
   CKF(cudaMalloc(&s->d_xw, (size_t)SATS_REF_GRID_BLOCKS * SATS_REF_GRID_THREADS * 6 * 4));
 #undef CKF
   *out = s;
@@ -355,7 +344,8 @@ static int set_attrs_once(sats_searcher *s)
     for (int b = 0; b < 3; b++)
       for (int lo = 0; lo < 2; lo++)
         for (int xw = 0; xw < 2; xw++)
-          CK(cudaFuncSetAttribute(pick_kernel(ws[a], ws[b], lo, xw), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+          for (int ls = 0; ls < 2; ls++)
+            CK(cudaFuncSetAttribute(pick_kernel(ws[a], ws[b], lo, xw, ls), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   s->attr_done = true;
   return SATS_OK;
 }
@@ -399,6 +389,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
   k.restarts = pp->restarts; k.lsoln = pp->lsoln; k.accept_mode = pp->accept_mode;
   k.seed_lo = (uint32_t)seed; k.seed_hi = (uint32_t)(seed >> 32);
   k.accept_tab = s->d_accept;
+  k.temps = s->d_accept + (size_t)SATS_K_MOVES * (SATS_K_DCLAMP + 1);
   k.out_scores = s->d_scores; k.out_maps = pp->lsoln ? s->d_maps : nullptr; k.out_stride = std::max(1, D);
   k.xw_states = s->d_xw; k.pool_list = s->d_pool_list; k.xw_blocks = s->d_xw_blocks;
 
@@ -430,13 +421,14 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
         k.sm_team_bytes = (int)round16(k.sm_entry_bytes + (size_t)k.sm_mapwords * k.tw * 4 * (pp->lsoln ? 2 : 1) + 64);
         size_t smem = 16 + k.sm_query_bytes + k.sm_nan_bytes + k.sm_team_bytes;
         if (smem > (size_t)kMaxSmem) return sats_fail(SATS_ERR_ARG, "query %d x entry order %d needs %zu B of shared memory", q, n2max, smem);
-        kernel_fn fn = pick_kernel(words_for(n1), words_for(n2max), pp->lorder != 0, true);
+        kernel_fn fn = pick_kernel(words_for(n1), words_for(n2max), pp->lorder != 0, true, pp->lsoln != 0);
         fn<<<dim3((unsigned)blocks.size(), 1), k.tw, smem, s->stream>>>(k);
         CK(cudaGetLastError());
         s->launches++;
       }
     } else {
-      const int tw_max = std::min(128, ((pp->restarts + 31) / 32) * 32);
+      int tw_max = std::min(128, ((pp->restarts + 31) / 32) * 32);
+      if (const char *e = getenv("SATS_TW")) { int t = atoi(e); if (t == 32 || t == 64 || t == 128) tw_max = std::min(tw_max, t); }
       CK(cudaEventRecord(s->fork, s->stream));
       for (int i = 0; i < sats_searcher::kSide; i++) CK(cudaStreamWaitEvent(s->side[i], s->fork, 0));
       int nlaunch = 0;
@@ -460,7 +452,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
           while (b1 < r1 && s->sorted_order[b1] > lowbound) b1++;
           k.sm_entry_bytes = (int)entry_blob_bytes(n2max);
           k.sm_nan_bytes = (int)round16(8 * (size_t)n2max);
-          kernel_fn fn = pick_kernel(w1, words_for(n2max), pp->lorder != 0, false);
+          kernel_fn fn = pick_kernel(w1, words_for(n2max), pp->lorder != 0, false, pp->lsoln != 0);
           // team width (threads sharing one entry; results do not depend on it) and teams per CTA: whatever keeps the
           // most warps resident per SM; a narrower team only when it buys strictly more
           int best_teams = 0, best_warps = -1, best_tw = 0, best_team_bytes = 0;

@@ -29,49 +29,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-#define SATS_K_MOVES 100
-#define SATS_K_DCLAMP 229          // expf(-d/T) <= 2^-33 (smallest uniform) for every d >= 229 and T <= 10
-#define SATS_K_NEG_INIT (-99999)
-#define SATS_K_ENTRY_HDR 80        // 16 B header + 4 types x 4 words of type masks
-#define SATS_K_QUERY_HDR 128       // 16 B header + 112 B of SSE types
-#define SATS_K_MAPROW 112          // bytes per (query, entry) row of the device map output
-
-struct SatsKParams {
-  // database (this GPU's shard), entries sorted by decreasing order
-  const uint8_t *blobs;            // entry blobs, each 16-byte aligned
-  const uint64_t *blob_off;        // byte offset of entry k
-  const uint32_t *blob_bytes;      // size of entry k's blob (multiple of 16)
-  // queries of this launch: blockIdx.y selects one
-  const uint8_t *qblobs;
-  const uint64_t *qblob_off;
-  const uint32_t *qblob_bytes;
-  int q_first;                     // index into qblob_* of blockIdx.y == 0
-  // work: Philox -> entries [item_first, item_first + item_count) of the sorted list, `teams` per CTA
-  //       XORWOW -> CTA c is reference block xw_blocks[c]; it walks pool_list[b], pool_list[b+128], ...
-  int item_first, item_count;
-  const int32_t *pool_list;        // XORWOW: pool position -> sorted entry index
-  int pool_count;
-  const int32_t *xw_blocks;
-  uint32_t *xw_states;             // 16384 x 6 words (d, v0..v4)
-  // geometry / shared-memory carve-up (bytes)
-  int tw;                          // threads per team
-  int teams;                       // teams per CTA
-  int sm_query_bytes;              // room for the largest query blob of this launch
-  int sm_entry_bytes;              // room for the largest entry blob of this launch
-  int sm_nan_bytes;                // room for one row of NaN-distance cells (8 B x largest entry order of this launch)
-  int sm_mapwords;                 // 32-bit words per chain map (n1max: one word per query SSE)
-  int sm_team_bytes;               // total per team
-  // search parameters
-  int restarts, lsoln, accept_mode;
-  uint32_t seed_lo, seed_hi;
-  const float *accept_tab;         // [SATS_K_MOVES][SATS_K_DCLAMP + 1]
-  // outputs, indexed [query slot][sorted entry index]
-  int32_t *out_scores;
-  int8_t *out_maps;                // rows of SATS_K_MAPROW bytes, or nullptr
-  int out_stride;                  // entries per query slot
-};
-
-__constant__ float c_sats_temps[SATS_K_MOVES];   // T_m = 10 * 0.95^m accumulated in fp32 like kernel.cu:1189
+#include "sats.h"
+#include "sats_kparams.h"
 
 namespace satsk {
 
@@ -286,7 +245,7 @@ __device__ __forceinline__ void map_put(uint32_t base, int k, uint32_t stride, i
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (uint32_t)k * stride), "r"(v) : "memory");
 }
 
-template <int W1, int W2, bool LORDER, bool XORWOW>
+template <int W1, int W2, bool LORDER, bool XORWOW, bool LSOLN>
 struct Chain {
   uint32_t mq[W1];   // query SSEs currently mapped
   uint32_t md[W2];   // entry SSEs currently occupied
@@ -299,6 +258,7 @@ struct Chain {
     for (int w = 0; w < W1; w++) mq[w] = 0u;
 #pragma unroll
     for (int w = 0; w < W2; w++) md[w] = 0u;
+#pragma unroll 1
     for (int k = 0; k < v.n1; k++) map_put(v.smap, k, v.mstride, -8);
     int next_j = 0;
     for (int i = 0; i < v.n1; i++) {
@@ -417,7 +377,8 @@ struct Chain {
     if (cand_score > best) {
       best = cand_score;
       best_tag = tag;
-      if (p.lsoln) {
+      if (LSOLN) {
+#pragma unroll 1                               // rare path: keep it small, the instruction cache is better spent on the move
         for (int k = 0; k < v.n1; k++) map_put(v.bmap, k, v.mstride, map_get(v.smap, k, v.mstride));
         map_put(v.bmap, i, v.mstride, to * 8);     // -1 -> -8
       }
@@ -425,7 +386,7 @@ struct Chain {
     const float u = u3();
     bool accept;
     if (p.accept_mode == SATS_ACCEPT_DEVICE_FAST) {
-      accept = __expf(__fdividef((float)d, c_sats_temps[m])) > u;
+      accept = __expf(__fdividef((float)d, __ldg(p.temps + m))) > u;
     } else if (d > 0) {
       accept = true;
     } else if (d == 0) {
@@ -445,12 +406,12 @@ struct Chain {
 };
 
 // Runs every chain this thread owns for one (query, entry) pair, then the team arg-max and the output.
-template <int W1, int W2, bool LORDER, bool XORWOW>
+template <int W1, int W2, bool LORDER, bool XORWOW, bool LSOLN>
 __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamView &v, int team, int tl, uint64_t *red,
                                              uint32_t entry_orig, uint32_t query_index, Xorwow &xw,
                                              int out_slot, int entry_sorted)
 {
-  Chain<W1, W2, LORDER, XORWOW> ch;
+  Chain<W1, W2, LORDER, XORWOW, LSOLN> ch;
   int best = SATS_K_NEG_INIT;
   int best_tag = tl;                                  // XORWOW: thread id; Philox: restart index of the best chain
   const int chains = XORWOW ? ((p.restarts + p.tw - 1) / p.tw) * p.tw : p.restarts;
@@ -478,8 +439,10 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
     if (ch.score > best) {
       best = ch.score;
       best_tag = tag;
-      if (p.lsoln)
+      if (LSOLN) {
+#pragma unroll 1
         for (int k = 0; k < v.n1; k++) map_put(v.bmap, k, v.mstride, map_get(v.smap, k, v.mstride));
+      }
     }
     if (XORWOW) {
       for (int m = 0; m < SATS_K_MOVES; m++)
@@ -512,8 +475,9 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
   const int team_best = (int)(uint32_t)(key >> 32) - 0x40000000;
   const unsigned team_tag = ~(uint32_t)key;
   if (tl == 0) p.out_scores[(size_t)out_slot * p.out_stride + entry_sorted] = team_best;
-  if (p.lsoln && best == team_best && (unsigned)best_tag == team_tag) {
+  if (LSOLN && best == team_best && (unsigned)best_tag == team_tag) {
     int8_t *row = p.out_maps + ((size_t)out_slot * p.out_stride + entry_sorted) * SATS_K_MAPROW;
+#pragma unroll 1
     for (int k = 0; k < v.n1; k++) row[k] = (int8_t)(map_get(v.bmap, k, v.mstride) >> 3);    // -8 -> -1 = unmapped
   }
   team_sync(team, p.tw);     // red[] and the entry buffer may be reused after this
@@ -526,11 +490,7 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
 //   [16, 16 + sm_query_bytes)   query blob (header + SSE types only when W1 == 4)
 //   then sm_nan_bytes           one row of {NaN, 0} cells
 //   then per team: entry blob (sm_entry_bytes) | maps (mapwords*tw*4) | best maps (same, if lsoln) | 64 B reduce scratch
-#ifndef SATS_K_MAXTHREADS
-#define SATS_K_MAXTHREADS 384
-#define SATS_K_MINBLOCKS 3
-#endif
-template <int W1, int W2, bool LORDER, bool XORWOW>
+template <int W1, int W2, bool LORDER, bool XORWOW, bool LSOLN>
 __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anneal_kernel(const SatsKParams p)
 {
   using namespace satsk;
@@ -544,7 +504,7 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
   uint8_t *smaps = se + p.sm_entry_bytes;
   const int mapbytes = p.sm_mapwords * p.tw * 4;
   uint8_t *bmaps = smaps + mapbytes;
-  uint64_t *red = reinterpret_cast<uint64_t *>(bmaps + (p.lsoln ? mapbytes : 0));
+  uint64_t *red = reinterpret_cast<uint64_t *>(bmaps + (LSOLN ? mapbytes : 0));
 
   const int qi = p.q_first + blockIdx.y;     // query slot of this batch: selects the blob and the output row
   if (threadIdx.x == 0) mbar_init(bar, 1);
@@ -586,7 +546,7 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
     const int32_t *eh = reinterpret_cast<const int32_t *>(se);
     v.n1 = qh[0];
     v.n2 = eh[0];
-    anneal_entry<W1, W2, LORDER, false>(p, v, team, tl, red, (uint32_t)eh[1], (uint32_t)qh[1], xw, qi, first + team);
+    anneal_entry<W1, W2, LORDER, false, LSOLN>(p, v, team, tl, red, (uint32_t)eh[1], (uint32_t)qh[1], xw, qi, first + team);
   } else {
     // validation: this CTA is reference block b; one team of 128 threads; entries b, b+128, ... in pool order
     const int b = p.xw_blocks[blockIdx.x];
@@ -612,7 +572,7 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
       phase ^= 1u;
       const int32_t *eh = reinterpret_cast<const int32_t *>(se);
       v.n2 = eh[0];
-      anneal_entry<W1, W2, LORDER, true>(p, v, 0, tl, red, (uint32_t)eh[1], (uint32_t)qh[1], xw, qi, e);
+      anneal_entry<W1, W2, LORDER, true, LSOLN>(p, v, 0, tl, red, (uint32_t)eh[1], (uint32_t)qh[1], xw, qi, e);
     }
     xw.store(st);
   }

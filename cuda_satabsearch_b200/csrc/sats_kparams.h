@@ -1,0 +1,62 @@
+// sats_kparams.h -- launch parameters and layout constants shared by the kernel translation units
+// (sats_kernels.cu, compiled once per query mask width) and the dispatcher (sats_device.cu).
+#ifndef SATS_KPARAMS_H
+#define SATS_KPARAMS_H
+
+#include <cstdint>
+
+#define SATS_K_MOVES 100
+#define SATS_K_DCLAMP 229          // expf(-d/T) <= 2^-33 (smallest uniform) for every d >= 229 and T <= 10
+#define SATS_K_NEG_INIT (-99999)
+#define SATS_K_ENTRY_HDR 80        // 16 B header + 4 types x 4 words of type masks
+#define SATS_K_QUERY_HDR 128       // 16 B header + 112 B of SSE types
+#define SATS_K_MAPROW 112          // bytes per (query, entry) row of the device map output
+
+struct SatsKParams {
+  // database (this GPU's shard), entries sorted by decreasing order
+  const uint8_t *blobs;            // entry blobs, each 16-byte aligned
+  const uint64_t *blob_off;        // byte offset of entry k
+  const uint32_t *blob_bytes;      // size of entry k's blob (multiple of 16)
+  // queries of this launch: blockIdx.y selects one
+  const uint8_t *qblobs;
+  const uint64_t *qblob_off;
+  const uint32_t *qblob_bytes;
+  int q_first;                     // index into qblob_* of blockIdx.y == 0
+  // work: Philox -> entries [item_first, item_first + item_count) of the sorted list, `teams` per CTA
+  //       XORWOW -> CTA c is reference block xw_blocks[c]; it walks pool_list[b], pool_list[b+128], ...
+  int item_first, item_count;
+  const int32_t *pool_list;        // XORWOW: pool position -> sorted entry index
+  int pool_count;
+  const int32_t *xw_blocks;
+  uint32_t *xw_states;             // 16384 x 6 words (d, v0..v4)
+  // geometry / shared-memory carve-up (bytes)
+  int tw;                          // threads per team
+  int teams;                       // teams per CTA
+  int sm_query_bytes;              // room for the largest query blob of this launch
+  int sm_entry_bytes;              // room for the largest entry blob of this launch
+  int sm_nan_bytes;                // room for one row of NaN-distance cells (8 B x largest entry order of this launch)
+  int sm_mapwords;                 // 32-bit words per chain map (n1max: one word per query SSE)
+  int sm_team_bytes;               // total per team
+  // search parameters
+  int restarts, lsoln, accept_mode;
+  uint32_t seed_lo, seed_hi;
+  const float *accept_tab;         // [SATS_K_MOVES][SATS_K_DCLAMP + 1]
+  const float *temps;              // [SATS_K_MOVES]: T_m = 10 * 0.95^m accumulated in fp32 like kernel.cu:1189
+  // outputs, indexed [query slot][sorted entry index]
+  int32_t *out_scores;
+  int8_t *out_maps;                // rows of SATS_K_MAPROW bytes, or nullptr
+  int out_stride;                  // entries per query slot
+};
+
+#ifndef SATS_K_MAXTHREADS
+#define SATS_K_MAXTHREADS 384
+#define SATS_K_MINBLOCKS 3
+#endif
+
+typedef void (*sats_kernel_fn)(const SatsKParams);
+// one definition per query mask width W1 (32-bit words: 1, 2 or 4), each in its own translation unit
+sats_kernel_fn sats_pick_kernel_w1(int w2, bool lorder, bool xorwow, bool lsoln);
+sats_kernel_fn sats_pick_kernel_w2(int w2, bool lorder, bool xorwow, bool lsoln);
+sats_kernel_fn sats_pick_kernel_w4(int w2, bool lorder, bool xorwow, bool lsoln);
+
+#endif  // SATS_KPARAMS_H
