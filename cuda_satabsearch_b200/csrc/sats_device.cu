@@ -62,6 +62,8 @@ struct sats_searcher {
   uint64_t xw_seed = 0;
   int32_t *d_pool_list = nullptr;
   int32_t *d_xw_blocks = nullptr;
+  int num_sms = 148;
+  int *d_counters = nullptr; size_t counter_cap = 0;   // one work counter per (bucket launch, query) of a search
   // queries
   uint8_t *d_qblobs = nullptr; size_t qblob_cap = 0;
   uint64_t *d_qoff = nullptr; uint32_t *d_qbytes = nullptr; int qmeta_cap = 0;
@@ -129,6 +131,7 @@ extern "C" int sats_searcher_create(const sats_db *db, int device, int shard_ran
 
   sats_searcher *s = new sats_searcher();
   s->device = device;
+  s->num_sms = prop.multiProcessorCount;
   s->db_count = db->count();
   std::vector<int32_t> owner((size_t)db->count(), 0);
   if (shard_count > 1) sats_partition(db, shard_count, owner.data());
@@ -203,7 +206,7 @@ extern "C" void sats_searcher_free(sats_searcher *s)
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
   cudaFree(s->d_blobs); cudaFree(s->d_blob_off); cudaFree(s->d_blob_bytes); cudaFree(s->d_accept); cudaFree(s->d_xw);
-  cudaFree(s->d_pool_list); cudaFree(s->d_xw_blocks); cudaFree(s->d_qblobs); cudaFree(s->d_qoff); cudaFree(s->d_qbytes);
+  cudaFree(s->d_pool_list); cudaFree(s->d_xw_blocks); cudaFree(s->d_counters); cudaFree(s->d_qblobs); cudaFree(s->d_qoff); cudaFree(s->d_qbytes);
   cudaFree(s->d_scores); cudaFree(s->d_maps); cudaFree(s->d_topk); cudaFreeHost(s->h_topk);
   cudaFreeHost(s->h_qstage); cudaFreeHost(s->h_scores); cudaFreeHost(s->h_maps);
   if (s->ev0) cudaEventDestroy(s->ev0);
@@ -419,7 +422,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
         k.sm_query_bytes = words_for(n1) > 2 ? SATS_K_QUERY_HDR : (int)s->q_bytes[q];
         k.sm_mapwords = n1;
         k.sm_team_bytes = (int)round16(k.sm_entry_bytes + (size_t)k.sm_mapwords * k.tw * 4 * (pp->lsoln ? 2 : 1) + 64);
-        size_t smem = 16 + k.sm_query_bytes + k.sm_nan_bytes + k.sm_team_bytes;
+        size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + k.sm_nan_bytes + k.sm_team_bytes;
         if (smem > (size_t)kMaxSmem) return sats_fail(SATS_ERR_ARG, "query %d x entry order %d needs %zu B of shared memory", q, n2max, smem);
         kernel_fn fn = pick_kernel(words_for(n1), words_for(n2max), pp->lorder != 0, true, pp->lsoln != 0);
         fn<<<dim3((unsigned)blocks.size(), 1), k.tw, smem, s->stream>>>(k);
@@ -427,6 +430,14 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
         s->launches++;
       }
     } else {
+      const size_t ncounters = (size_t)Q * (sizeof kBucketBounds / sizeof kBucketBounds[0]);
+      if (ncounters > s->counter_cap) {
+        cudaFree(s->d_counters); s->d_counters = nullptr; s->counter_cap = 0;
+        CK(cudaMalloc(&s->d_counters, ncounters * sizeof(int)));
+        s->counter_cap = ncounters;
+      }
+      CK(cudaMemsetAsync(s->d_counters, 0, ncounters * sizeof(int), s->stream));
+      size_t counter_base = 0;
       int tw_max = std::min(128, ((pp->restarts + 31) / 32) * 32);
       if (const char *e = getenv("SATS_TW")) { int t = atoi(e); if (t == 32 || t == 64 || t == 128) tw_max = std::min(tw_max, t); }
       CK(cudaEventRecord(s->fork, s->stream));
@@ -455,17 +466,19 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
           kernel_fn fn = pick_kernel(w1, words_for(n2max), pp->lorder != 0, false, pp->lsoln != 0);
           // team width (threads sharing one entry; results do not depend on it) and teams per CTA: whatever keeps the
           // most warps resident per SM; a narrower team only when it buys strictly more
-          int best_teams = 0, best_warps = -1, best_tw = 0, best_team_bytes = 0;
+          int best_teams = 0, best_warps = -1, best_tw = 0, best_team_bytes = 0, best_ctas = 0;
           for (int tw = tw_max; tw >= 32; tw >>= 1) {
             if (tw & 31) continue;             // 96 -> 48: not a whole number of warps
             const int team_bytes = (int)round16(k.sm_entry_bytes + (size_t)k.sm_mapwords * tw * 4 * (pp->lsoln ? 2 : 1) + 64);
-            for (int teams = SATS_K_MAXTHREADS / tw; teams >= 1; teams--) {
-              size_t smem = 16 + k.sm_query_bytes + k.sm_nan_bytes + (size_t)teams * team_bytes;
+            int teams_max = SATS_K_MAXTHREADS / tw;
+            if (const char *e = getenv("SATS_TEAMS")) teams_max = std::max(1, std::min(teams_max, atoi(e)));
+            for (int teams = teams_max; teams >= 1; teams--) {
+              size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + k.sm_nan_bytes + (size_t)teams * team_bytes;
               if (smem > (size_t)kMaxSmem) continue;
               int ctas = 0;
               CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, fn, teams * tw, smem));
               int warps = ctas * teams * tw / 32;
-              if (warps > best_warps) { best_warps = warps; best_teams = teams; best_tw = tw; best_team_bytes = team_bytes; }
+              if (warps > best_warps) { best_warps = warps; best_teams = teams; best_tw = tw; best_team_bytes = team_bytes; best_ctas = ctas; }
             }
           }
           if (best_teams == 0) return sats_fail(SATS_ERR_ARG, "query order %d x entry order %d does not fit in shared memory", n1max, n2max);
@@ -474,8 +487,12 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
           k.teams = best_teams;
           k.sm_team_bytes = best_team_bytes;
           k.item_first = b0; k.item_count = b1 - b0;
-          size_t smem = 16 + k.sm_query_bytes + k.sm_nan_bytes + (size_t)k.teams * k.sm_team_bytes;
-          dim3 grid((unsigned)((k.item_count + k.teams - 1) / k.teams), (unsigned)(q1 - q0));
+          size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + k.sm_nan_bytes + (size_t)k.teams * k.sm_team_bytes;
+          // persistent teams: no more CTAs than fit on the device at once (per query); each team keeps claiming entries
+          k.counters = s->d_counters + counter_base;
+          counter_base += (size_t)(q1 - q0);
+          const int resident = std::max(1, best_ctas) * s->num_sms;
+          dim3 grid((unsigned)std::min((k.item_count + k.teams - 1) / k.teams, resident), (unsigned)(q1 - q0));
           fn<<<grid, k.teams * tw, smem, s->side[nlaunch % sats_searcher::kSide]>>>(k);
           CK(cudaGetLastError());
           s->launches++;

@@ -486,8 +486,8 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
 }  // namespace satsk
 
 // Shared-memory layout of a CTA:
-//   [0,16)                      mbarrier
-//   [16, 16 + sm_query_bytes)   query blob (header + SSE types only when W1 == 4)
+//   [0, 128)                    mbarriers: one for the query, one per team
+//   then sm_query_bytes         query blob (header + SSE types only when W1 == 4)
 //   then sm_nan_bytes           one row of {NaN, 0} cells
 //   then per team: entry blob (sm_entry_bytes) | maps (mapwords*tw*4) | best maps (same, if lsoln) | 64 B reduce scratch
 template <int W1, int W2, bool LORDER, bool XORWOW, bool LSOLN>
@@ -495,11 +495,11 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
 {
   using namespace satsk;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
-  uint8_t *sq = smem + 16;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem);       // bar[0]: query (and XORWOW entries); bar[1 + team]: that team's entries
+  uint8_t *sq = smem + SATS_K_BAR_BYTES;
   uint2 *snan = reinterpret_cast<uint2 *>(sq + p.sm_query_bytes);
   const int team = threadIdx.x / p.tw, tl = threadIdx.x - team * p.tw;
-  uint8_t *steam = smem + 16 + p.sm_query_bytes + p.sm_nan_bytes + (size_t)team * p.sm_team_bytes;
+  uint8_t *steam = smem + SATS_K_BAR_BYTES + p.sm_query_bytes + p.sm_nan_bytes + (size_t)team * p.sm_team_bytes;
   uint8_t *se = steam;
   uint8_t *smaps = se + p.sm_entry_bytes;
   const int mapbytes = p.sm_mapwords * p.tw * 4;
@@ -507,7 +507,8 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
   uint64_t *red = reinterpret_cast<uint64_t *>(bmaps + (LSOLN ? mapbytes : 0));
 
   const int qi = p.q_first + blockIdx.y;     // query slot of this batch: selects the blob and the output row
-  if (threadIdx.x == 0) mbar_init(bar, 1);
+  if (threadIdx.x == 0)
+    for (int t = 0; t <= p.teams; t++) mbar_init(bar + t, 1);
   for (int c = threadIdx.x; c < (p.sm_nan_bytes >> 3); c += blockDim.x) snan[c] = make_uint2(0x7fc00000u, 0u);
   __syncthreads();
 
@@ -527,26 +528,42 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
   Xorwow xw;
 
   if (!XORWOW) {
-    // one pass: team t anneals sorted entry item_first + blockIdx.x * teams + t
-    const int first = p.item_first + blockIdx.x * p.teams;
-    const int here = min(p.teams, p.item_first + p.item_count - first);
+    // Persistent teams: the query is staged once per CTA; after that every team works on its own -- its leader claims
+    // the next entry of this launch's (decreasing-order) list from a global counter, brings the blob in with one TMA
+    // bulk copy on the team's own mbarrier, the team anneals it, and so on until the list is exhausted.  No CTA-wide
+    // synchronisation after the prologue, so a slow entry holds up only its own team.
     if (threadIdx.x == 0) {
       const uint32_t qbytes = W1 > 2 ? (uint32_t)SATS_K_QUERY_HDR : p.qblob_bytes[qi];
-      uint32_t total = qbytes;
-      for (int t = 0; t < here; t++) total += p.blob_bytes[first + t];
-      mbar_expect_tx(bar, total);
+      mbar_expect_tx(bar, qbytes);
       tma_load_1d(sq, p.qblobs + p.qblob_off[qi], qbytes, bar);
-      for (int t = 0; t < here; t++)
-        tma_load_1d(smem + 16 + p.sm_query_bytes + p.sm_nan_bytes + (size_t)t * p.sm_team_bytes, p.blobs + p.blob_off[first + t],
-                    p.blob_bytes[first + t], bar);
     }
     mbar_wait(bar, 0);
-    if (team >= here) return;
     const int32_t *qh = reinterpret_cast<const int32_t *>(sq);
     const int32_t *eh = reinterpret_cast<const int32_t *>(se);
     v.n1 = qh[0];
-    v.n2 = eh[0];
-    anneal_entry<W1, W2, LORDER, false, LSOLN>(p, v, team, tl, red, (uint32_t)eh[1], (uint32_t)qh[1], xw, qi, first + team);
+    uint64_t *tbar = bar + 1 + team;
+    volatile int *claim = reinterpret_cast<volatile int *>(red + 4);      // red[0..3]: arg-max scratch of the team's warps
+    int *counter = p.counters + blockIdx.y;
+    uint32_t phase = 0;
+    for (;;) {
+      if (tl == 0) {
+        const int idx = atomicAdd(counter, 1);
+        *claim = idx;
+        if (idx < p.item_count) {
+          const int e = p.item_first + idx;
+          const uint32_t bytes = p.blob_bytes[e];
+          mbar_expect_tx(tbar, bytes);
+          tma_load_1d(se, p.blobs + p.blob_off[e], bytes, tbar);
+        }
+      }
+      team_sync(team, p.tw);
+      const int idx = *claim;
+      if (idx >= p.item_count) break;
+      mbar_wait(tbar, phase);
+      phase ^= 1u;
+      v.n2 = eh[0];
+      anneal_entry<W1, W2, LORDER, false, LSOLN>(p, v, team, tl, red, (uint32_t)eh[1], (uint32_t)qh[1], xw, qi, p.item_first + idx);
+    }
   } else {
     // validation: this CTA is reference block b; one team of 128 threads; entries b, b+128, ... in pool order
     const int b = p.xw_blocks[blockIdx.x];

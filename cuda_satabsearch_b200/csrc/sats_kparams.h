@@ -10,6 +10,7 @@
 #define SATS_K_NEG_INIT (-99999)
 #define SATS_K_ENTRY_HDR 80        // 16 B header + 4 types x 4 words of type masks
 #define SATS_K_QUERY_HDR 128       // 16 B header + 112 B of SSE types
+#define SATS_K_BAR_BYTES 128       // shared-memory header: 1 + teams mbarriers (teams <= 12)
 #define SATS_K_MAPROW 112          // bytes per (query, entry) row of the device map output
 
 struct SatsKParams {
@@ -22,9 +23,11 @@ struct SatsKParams {
   const uint64_t *qblob_off;
   const uint32_t *qblob_bytes;
   int q_first;                     // index into qblob_* of blockIdx.y == 0
-  // work: Philox -> entries [item_first, item_first + item_count) of the sorted list, `teams` per CTA
+  // work: Philox -> entries [item_first, item_first + item_count) of the sorted list, claimed one at a time by the
+  //       teams of all CTAs through counters[blockIdx.y] (zeroed before the launch)
   //       XORWOW -> CTA c is reference block xw_blocks[c]; it walks pool_list[b], pool_list[b+128], ...
   int item_first, item_count;
+  int *counters;
   const int32_t *pool_list;        // XORWOW: pool position -> sorted entry index
   int pool_count;
   const int32_t *xw_blocks;
