@@ -110,7 +110,7 @@ __device__ __forceinline__ int top_bit(uint32_t x)
   asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
   return r;
 }
-// mask of bit positions < n, 0 <= n <= 31: one BMSK
+// mask of bit positions < n, 0 <= n <= 32: one BMSK
 __device__ __forceinline__ uint32_t bits_below(int n)
 {
   uint32_t r;
@@ -118,20 +118,22 @@ __device__ __forceinline__ uint32_t bits_below(int n)
   return r;
 }
 
-// highest set bit with index <= i, or -1
+// highest set bit with index <= i, or -1 (0 <= i < 32 W).  bfind of 0 is -1, so one word needs no select at all.
 template <int W> __device__ __forceinline__ int top_at_or_below(const uint32_t (&m)[W], int i)
 {
+  if (W == 1) return top_bit(m[0] & bits_below(i + 1));
   int r = -1;
 #pragma unroll
   for (int w = 0; w < W; w++) {
     uint32_t x = m[w] & below(i + 1 - 32 * w);
-    if (x) r = 32 * w + 31 - __clz(x);
+    if (x) r = 32 * w + top_bit(x);
   }
   return r;
 }
-// lowest set bit with index >= i, or -1
+// lowest set bit with index >= i, or -1 (0 <= i <= 32 W)
 template <int W> __device__ __forceinline__ int low_at_or_above(const uint32_t (&m)[W], int i)
 {
+  if (W == 1) return __ffs(m[0] & ~bits_below(i)) - 1;
   int r = -1;
 #pragma unroll
   for (int w = W - 1; w >= 0; w--) {
