@@ -420,8 +420,9 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
         const int n1 = s->q_n1[q];
         k.q_first = q;
         k.sm_query_bytes = words_for(n1) > 2 ? SATS_K_QUERY_HDR : (int)s->q_bytes[q];
-        k.sm_mapwords = n1;
-        k.sm_team_bytes = (int)round16(k.sm_entry_bytes + (size_t)k.sm_mapwords * k.tw * 4 * (pp->lsoln ? 2 : 1) + 64);
+        k.sm_mapwords = words_for(n1) > 2 ? (n1 + 3) / 4 : ((n1 + 3) & ~3);
+        k.sm_bmapwords = pp->lsoln ? (n1 + 3) / 4 : 0;
+        k.sm_team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * k.tw * 4 + 64);
         size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + k.sm_nan_bytes + k.sm_team_bytes;
         if (smem > (size_t)kMaxSmem) return sats_fail(SATS_ERR_ARG, "query %d x entry order %d needs %zu B of shared memory", q, n2max, smem);
         kernel_fn fn = pick_kernel(words_for(n1), words_for(n2max), pp->lorder != 0, true, pp->lsoln != 0);
@@ -452,7 +453,8 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
         for (int q = q0; q < q1; q++) { n1max = std::max(n1max, s->q_n1[q]); qbmax = std::max(qbmax, s->q_bytes[q]); }
         k.q_first = q0;
         k.sm_query_bytes = w1 > 2 ? SATS_K_QUERY_HDR : (int)qbmax;
-        k.sm_mapwords = n1max;
+        k.sm_mapwords = w1 > 2 ? (n1max + 3) / 4 : ((n1max + 3) & ~3);     // whole groups of four: map_save reads them so
+        k.sm_bmapwords = pp->lsoln ? (n1max + 3) / 4 : 0;
         int b0 = r0;
         while (b0 < r1) {
           // bucket = maximal run of entries whose order falls under the same bound (list is decreasing)
@@ -469,7 +471,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
           int best_teams = 0, best_warps = -1, best_tw = 0, best_team_bytes = 0, best_ctas = 0;
           for (int tw = tw_max; tw >= 32; tw >>= 1) {
             if (tw & 31) continue;             // 96 -> 48: not a whole number of warps
-            const int team_bytes = (int)round16(k.sm_entry_bytes + (size_t)k.sm_mapwords * tw * 4 * (pp->lsoln ? 2 : 1) + 64);
+            const int team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * tw * 4 + 64);
             int teams_max = SATS_K_MAXTHREADS / tw;
             if (const char *e = getenv("SATS_TEAMS")) teams_max = std::max(1, std::min(teams_max, atoi(e)));
             for (int teams = teams_max; teams >= 1; teams--) {

@@ -230,28 +230,81 @@ struct TeamView {
   uint32_t ecell;          // n2 x n2
   uint32_t nanrow;         // one row of cells whose distance is NaN: stands in for the missing side of a move
   const uint32_t *tmask;   // [4][4] type -> 128-bit mask of entry SSEs of that type
-  uint32_t smap;           // this lane's map: word k at smap + k * mstride holds 8 * partner (or -8 = unmapped)
-  uint32_t bmap;           // best map, same addressing
+  uint32_t smap;           // this lane's live map (Map<W1 <= 2>)
+  uint32_t bmap;           // this lane's best map (Map<false>)
   uint32_t mstride;        // tw * 4: consecutive lanes own consecutive banks, so lane-private accesses never conflict
   int n1, n2, tw;
 };
 
-__device__ __forceinline__ int map_get(uint32_t base, int k, uint32_t stride)
-{
-  int v;
-  asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)k * stride) : "memory");
-  return v;
-}
-__device__ __forceinline__ void map_put(uint32_t base, int k, uint32_t stride, int v)
-{
-  asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (uint32_t)k * stride), "r"(v) : "memory");
-}
-
+// Lane-private maps (query SSE -> partner entry SSE) in two representations, both laid out so that consecutive lanes own
+// consecutive banks (stride = tw * 4 bytes between a lane's successive words):
+//   Map<true>   one 32-bit word per query SSE holding 8 * partner (-8 = unmapped): one IMAD to address, and the value is
+//               already the byte offset of the partner's cell in a row.  Used for the live map of queries of <= 64 SSEs.
+//   Map<false>  one byte per query SSE (0xff = unmapped), four to a word.  A quarter of the shared memory, three more
+//               instructions per access: used for the live map of larger queries and for every best-so-far map.
+template <bool WIDE> struct Map {
+  static __device__ __forceinline__ uint32_t addr(uint32_t base, int k, uint32_t stride)
+  {
+    if (WIDE) return base + (uint32_t)k * stride;
+    return (uint32_t)(k >> 2) * stride + (base | (uint32_t)(k & 3));      // the lane's slot is 4-byte aligned
+  }
+  // 8 * partner of a MAPPED query SSE
+  static __device__ __forceinline__ uint32_t off8(uint32_t base, int k, uint32_t stride)
+  {
+    uint32_t v;
+    if (WIDE) asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory");
+    else { asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory"); v <<= 3; }
+    return v;
+  }
+  // partner of a query SSE, -1 if unmapped
+  static __device__ __forceinline__ int get(uint32_t base, int k, uint32_t stride)
+  {
+    int v;
+    if (WIDE) { asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory"); return v >> 3; }
+    asm("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory");
+    return v;
+  }
+  static __device__ __forceinline__ void put(uint32_t base, int k, uint32_t stride, int j)      // j = -1 unmaps
+  {
+    if (WIDE) asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr(base, k, stride)), "r"(j * 8) : "memory");
+    else asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr(base, k, stride)), "r"(j) : "memory");
+  }
+  static __device__ __forceinline__ int words(int n1) { return WIDE ? n1 : (n1 + 3) >> 2; }
+  static __device__ __forceinline__ void clear(uint32_t base, int n1, uint32_t stride)
+  {
+#pragma unroll 1
+    for (int w = 0; w < words(n1); w++)
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (uint32_t)w * stride), "r"(WIDE ? -8 : -1) : "memory");
+  }
+};
 template <int W1, int W2, bool LORDER, bool XORWOW, bool LSOLN>
 struct Chain {
+  typedef Map<(W1 <= 2)> LiveMap;
   uint32_t mq[W1];   // query SSEs currently mapped
   uint32_t md[W2];   // entry SSEs currently occupied
   int score;
+  // LSOLN: the best map is never copied wholesale when the best score improves.  An improving move has d > 0 and is
+  // therefore accepted, so right after it best map == live map.  From then on the first accepted change of a query SSE
+  // saves that SSE's partner *as it was at the best moment* into v.bmap and marks the SSE dirty; so at any time
+  //     best map[k] = dirty[k] ? v.bmap[k] : live map[k],
+  // and the clean entries are filled in once, when the chain ends.  `owned`: this chain holds the lane's best so far
+  // (otherwise v.bmap still carries an earlier chain's best map and must not be touched).
+  uint32_t dirty[W1];
+  bool owned;
+
+  __device__ __forceinline__ void best_is_live()
+  {
+    owned = true;
+#pragma unroll
+    for (int w = 0; w < W1; w++) dirty[w] = 0u;
+  }
+  __device__ __forceinline__ void finish_best_map(const TeamView &v)
+  {
+    if (!owned) return;
+#pragma unroll 1
+    for (int k = 0; k < v.n1; k++)
+      if (!bit_test<W1>(dirty, k)) Map<false>::put(v.bmap, k, v.mstride, LiveMap::get(v.smap, k, v.mstride));
+  }
 
   // thinit (kernel.cu:588-648): walk the query, with probability 1/2 match SSE i to the next entry SSE of its type
   template <class Draw> __device__ __forceinline__ void seed(const TeamView &v, Draw &&draw)
@@ -260,8 +313,7 @@ struct Chain {
     for (int w = 0; w < W1; w++) mq[w] = 0u;
 #pragma unroll
     for (int w = 0; w < W2; w++) md[w] = 0u;
-#pragma unroll 1
-    for (int k = 0; k < v.n1; k++) map_put(v.smap, k, v.mstride, -8);
+    LiveMap::clear(v.smap, v.n1, v.mstride);
     int next_j = 0;
     for (int i = 0; i < v.n1; i++) {
       float u = draw(i);
@@ -272,7 +324,7 @@ struct Chain {
         for (int w = 0; w < W2; w++) cand[w] = tm[w];
         int j = low_at_or_above<W2>(cand, next_j);
         if (j < 0) break;
-        map_put(v.smap, i, v.mstride, j * 8);
+        LiveMap::put(v.smap, i, v.mstride, j);
         bit_set<W1>(mq, i);
         bit_set<W2>(md, j);
         next_j = j + 1;
@@ -290,7 +342,7 @@ struct Chain {
       while (bi) {
         int i = 32 * wi + __ffs(bi) - 1;
         bi &= bi - 1u;
-        const uint32_t erow = v.ecell + (uint32_t)(map_get(v.smap, i, v.mstride) * v.n2);
+        const uint32_t erow = v.ecell + LiveMap::off8(v.smap, i, v.mstride) * (uint32_t)v.n2;
         const uint32_t qrow = v.qcell + (uint32_t)(i * v.n1) * 8u;
         const uint2 *qrow_g = v.qcell_g + i * v.n1;
 #pragma unroll
@@ -302,7 +354,7 @@ struct Chain {
             int k = 32 * wk + __ffs(bk) - 1;
             bk &= bk - 1u;
             total += gated(W1 > 2 ? __ldg(qrow_g + k) : lds64(qrow + (uint32_t)k * 8u),
-                           lds64(erow + (uint32_t)map_get(v.smap, k, v.mstride)));
+                           lds64(erow + LiveMap::off8(v.smap, k, v.mstride)));
           }
         }
       }
@@ -329,7 +381,7 @@ struct Chain {
         const int z = top_bit(b);
         b &= bits_below(z);
         const int k = 32 * w + z;
-        const uint32_t l8 = (uint32_t)map_get(v.smap, k, v.mstride);
+        const uint32_t l8 = LiveMap::off8(v.smap, k, v.mstride);
         const uint2 q = W1 > 2 ? __ldg(qrow_g + k) : lds64(qrow + (uint32_t)k * 8u);
         const uint2 ef = lds64(frow + l8), et = lds64(trow + l8);
         d += gated(q, et) - gated(q, ef);
@@ -349,16 +401,16 @@ struct Chain {
     int lo, hi, from;
     if (LORDER) {
       int kp = top_at_or_below<W1>(mq, i);
-      lo = kp >= 0 ? map_get(v.smap, kp, v.mstride) >> 3 : v.n2;
+      lo = kp >= 0 ? LiveMap::get(v.smap, kp, v.mstride) : v.n2;
       from = was_mapped ? lo : -1;
       if (i == v.n1 - 1) hi = v.n2;
       else {
         int kn = low_at_or_above<W1>(mq, i + 1);
-        hi = kn >= 0 ? map_get(v.smap, kn, v.mstride) >> 3 : -1;
+        hi = kn >= 0 ? LiveMap::get(v.smap, kn, v.mstride) : -1;
       }
     } else {
       lo = 0; hi = v.n2;
-      from = was_mapped ? map_get(v.smap, i, v.mstride) >> 3 : -1;
+      from = was_mapped ? LiveMap::get(v.smap, i, v.mstride) : -1;
     }
     // randtypeind (kernel.cu:677-714): unoccupied entry SSEs of the right type inside [lo, hi)
     const uint32_t *tm = v.tmask + 4 * v.qtype[i];
@@ -376,14 +428,11 @@ struct Chain {
     int d = 0;
     if (from >= 0 || to >= 0) d = delta(v, i, from, to);
     const int cand_score = score + d;
-    if (cand_score > best) {
+    const bool improved = cand_score > best;
+    if (improved) {
       best = cand_score;
       best_tag = tag;
-      if (LSOLN) {
-#pragma unroll 1                               // rare path: keep it small, the instruction cache is better spent on the move
-        for (int k = 0; k < v.n1; k++) map_put(v.bmap, k, v.mstride, map_get(v.smap, k, v.mstride));
-        map_put(v.bmap, i, v.mstride, to * 8);     // -1 -> -8
-      }
+      if (LSOLN) best_is_live();
     }
     const float u = u3();
     bool accept;
@@ -402,7 +451,13 @@ struct Chain {
       if (from >= 0) bit_clear<W2>(md, from);
       if (to >= 0) { bit_set<W2>(md, to); bit_set<W1>(mq, i); }
       else bit_clear<W1>(mq, i);
-      if (from >= 0 || to >= 0) map_put(v.smap, i, v.mstride, to * 8);
+      if (from >= 0 || to >= 0) {
+        if (LSOLN && !improved && owned && !bit_test<W1>(dirty, i)) {
+          Map<false>::put(v.bmap, i, v.mstride, from);       // what SSE i was matched to when the best score was reached
+          bit_set<W1>(dirty, i);
+        }
+        LiveMap::put(v.smap, i, v.mstride, to);
+      }
     }
   }
 };
@@ -441,10 +496,9 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
     if (ch.score > best) {
       best = ch.score;
       best_tag = tag;
-      if (LSOLN) {
-#pragma unroll 1
-        for (int k = 0; k < v.n1; k++) map_put(v.bmap, k, v.mstride, map_get(v.smap, k, v.mstride));
-      }
+      if (LSOLN) ch.best_is_live();
+    } else {
+      ch.owned = false;
     }
     if (XORWOW) {
       for (int m = 0; m < SATS_K_MOVES; m++)
@@ -463,6 +517,7 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
         ch.move(v, m + 3, p, best, best_tag, tag, [&] { return unit_from_bits(c[1]); }, [&] { return unit_from_bits(c[2]); }, [&] { return unit_from_bits(c[3]); });
       }
     }
+    if (LSOLN) ch.finish_best_map(v);
   }
 
   // ---- arg-max over the team: highest score, lowest tag (kernel.cu:1205-1221 scans thread 0..127 with '>')
@@ -480,7 +535,11 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
   if (LSOLN && best == team_best && (unsigned)best_tag == team_tag) {
     int8_t *row = p.out_maps + ((size_t)out_slot * p.out_stride + entry_sorted) * SATS_K_MAPROW;
 #pragma unroll 1
-    for (int k = 0; k < v.n1; k++) row[k] = (int8_t)(map_get(v.bmap, k, v.mstride) >> 3);    // -8 -> -1 = unmapped
+    for (int w = 0; w < Map<false>::words(v.n1); w++) {
+      uint32_t x;
+      asm("ld.shared.b32 %0, [%1];" : "=r"(x) : "r"(v.bmap + (uint32_t)w * v.mstride) : "memory");
+      reinterpret_cast<uint32_t *>(row)[w] = x;
+    }
   }
   team_sync(team, p.tw);     // red[] and the entry buffer may be reused after this
 }
@@ -491,7 +550,7 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
 //   [0, 128)                    mbarriers: one for the query, one per team
 //   then sm_query_bytes         query blob (header + SSE types only when W1 == 4)
 //   then sm_nan_bytes           one row of {NaN, 0} cells
-//   then per team: entry blob (sm_entry_bytes) | maps (mapwords*tw*4) | best maps (same, if lsoln) | 64 B reduce scratch
+//   then per team: entry blob (sm_entry_bytes) | live maps (mapwords*tw*4) | best maps (bmapwords*tw*4) | 64 B reduce scratch
 template <int W1, int W2, bool LORDER, bool XORWOW, bool LSOLN>
 __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anneal_kernel(const SatsKParams p)
 {
@@ -504,9 +563,8 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
   uint8_t *steam = smem + SATS_K_BAR_BYTES + p.sm_query_bytes + p.sm_nan_bytes + (size_t)team * p.sm_team_bytes;
   uint8_t *se = steam;
   uint8_t *smaps = se + p.sm_entry_bytes;
-  const int mapbytes = p.sm_mapwords * p.tw * 4;
-  uint8_t *bmaps = smaps + mapbytes;
-  uint64_t *red = reinterpret_cast<uint64_t *>(bmaps + (LSOLN ? mapbytes : 0));
+  uint8_t *bmaps = smaps + p.sm_mapwords * p.tw * 4;
+  uint64_t *red = reinterpret_cast<uint64_t *>(bmaps + p.sm_bmapwords * p.tw * 4);
 
   const int qi = p.q_first + blockIdx.y;     // query slot of this batch: selects the blob and the output row
   if (threadIdx.x == 0)
