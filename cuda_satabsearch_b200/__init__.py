@@ -70,6 +70,7 @@ def _load() -> C.CDLL:
         "sats_searcher_get_xorwow": (ci, [vp, vp]), "sats_searcher_reset_xorwow": (ci, [vp, C.c_uint64]),
         "sats_device_count": (ci, []),
         "sats_search_topk": (ci, [vp, ci, vp, vp]),
+        "sats_search_hits": (ci, [vp, C.c_double, ci, vp, vp, vp]),
         "sats_results_parse": (ci, [cs, C.c_size_t, P(vp)]), "sats_results_free": (None, [vp]),
         "sats_results_blocks": (ci, [vp]), "sats_results_query": (cs, [vp, ci]), "sats_results_dbfile": (cs, [vp, ci]),
         "sats_results_flags": (ci, [vp, ci, P(ci)]), "sats_results_rows": (ci, [vp, ci]),
@@ -331,6 +332,16 @@ class Searcher:
         sc = np.full((q, k), np.iinfo(np.int32).min, np.int32)
         _check(lib().sats_search_topk(self._h, k, idx.ctypes.data, sc.ctypes.data))
         return idx, sc
+
+    def hits(self, z_min: float, cap: int):
+        """After launch(): device-side cut at Gumbel z-score >= z_min -> (counts int32 [q], index int32 [q, cap] original
+        db indices in device order, scores int32 [q, cap]); counts may exceed cap."""
+        q = self._qcount
+        cnt = np.zeros(q, np.int32)
+        idx = np.full((q, cap), -1, np.int32)
+        sc = np.full((q, cap), np.iinfo(np.int32).min, np.int32)
+        _check(lib().sats_search_hits(self._h, float(z_min), cap, cnt.ctypes.data, idx.ctypes.data, sc.ctypes.data))
+        return cnt, idx, sc
 
     def xorwow_states(self) -> np.ndarray:
         st = np.zeros((128 * 128, 6), np.uint32)

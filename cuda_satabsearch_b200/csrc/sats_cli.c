@@ -20,6 +20,8 @@
  *   -L        also search database structures of order 112..128 (the reference drops everything above 111)
  *   -k N      print only the N best-scoring structures of each (query, pool) block, best first (selected on the
  *             device with sats_search_topk, so only N rows per query leave the GPU); single GPU, LSOLN = F
+ *   -z Z      print only the structures whose z-score (4th column) is >= Z, in database order of decreasing size
+ *             (selected on the device with sats_search_hits); single GPU, LSOLN = F, not together with -k
  */
 #include <getopt.h>
 #include <stdio.h>
@@ -46,7 +48,7 @@ static void die(const char *what)
 
 static void usage(const char *prog)
 {
-  fprintf(stderr, "Usage: %s [-c] [-q dbfile] [-r restarts] [-g gpus] [-R philox|xorwow] [-A table|fast] [-s seed] [-k tophits] [-L]\n", prog);
+  fprintf(stderr, "Usage: %s [-c] [-q dbfile] [-r restarts] [-g gpus] [-R philox|xorwow] [-A table|fast] [-s seed] [-k tophits] [-z zmin] [-L]\n", prog);
   fprintf(stderr, "  -c : (reference: run on host CPU) not available in this build\n");
   fprintf(stderr, "  -q dbfile : database is read from dbfile, list of query\n"
                   "              ids is read from stdin\n");
@@ -89,12 +91,13 @@ int main(int argc, char *argv[])
 {
   char dbfile[4096] = "";
   int querydbmode = 0, maxstart = SATS_DEFAULT_MAXSTART, ngpus = 1, c;
-  int rng_mode = SATS_RNG_PHILOX, accept_mode = SATS_ACCEPT_HOST_TABLE, topk = 0, max_order = SATS_MAXDIM;
+  int rng_mode = SATS_RNG_PHILOX, accept_mode = SATS_ACCEPT_HOST_TABLE, topk = 0, max_order = SATS_MAXDIM, zcut = 0;
+  double zmin = 0.0;
   unsigned long long seed = SATS_REF_SEED;
   int flags[3] = {1, 1, 0};
   sats_db *db = NULL, *queries = NULL;
 
-  while ((c = getopt(argc, argv, "cq:r:g:R:A:s:k:L")) != -1) {
+  while ((c = getopt(argc, argv, "cq:r:g:R:A:s:k:z:L")) != -1) {
     switch (c) {
       case 'c':
         fprintf(stderr, "ERROR: -c (host CPU search) is not available: this build is GPU-only\n");
@@ -114,6 +117,7 @@ int main(int argc, char *argv[])
         break;
       case 's': seed = strtoull(optarg, NULL, 0); break;
       case 'k': topk = atoi(optarg); break;
+      case 'z': zcut = 1; zmin = atof(optarg); break;
       case 'L': max_order = SATS_MAXDIM_EXT; break;
       default: usage(argv[0]);
     }
@@ -125,6 +129,7 @@ int main(int argc, char *argv[])
     exit(1);
   }
   if (topk < 0 || (topk > 0 && ngpus > 1)) { fprintf(stderr, "ERROR: -k needs a positive count and a single GPU\n"); exit(1); }
+  if (zcut && (ngpus > 1 || topk > 0)) { fprintf(stderr, "ERROR: -z needs a single GPU and cannot be combined with -k\n"); exit(1); }
   fprintf(stderr, "MAXDIM = %d\n", max_order);
 
   size_t inlen = 0;
@@ -154,7 +159,7 @@ int main(int argc, char *argv[])
     flags[0] = 1;
   }
   const int lorder = flags[1], lsoln = flags[2];
-  if (topk > 0 && lsoln) { fprintf(stderr, "ERROR: -k cannot be combined with LSOLN = T\n"); exit(1); }
+  if ((topk > 0 || zcut) && lsoln) { fprintf(stderr, "ERROR: -k / -z cannot be combined with LSOLN = T\n"); exit(1); }
 
   fprintf(stderr, "Loading database...\n");
   double t0 = now_ms();
@@ -221,12 +226,17 @@ int main(int argc, char *argv[])
         if (sats_search_upload(sr[g], queries, q0, nq) != SATS_OK) die("ERROR uploading queries");
       for (int g = 0; g < ngpus; g++)
         if (sats_search_launch(sr[g], &prm, (uint32_t)q0, NULL) != SATS_OK) die("kernel launch failed");
-      int32_t *top_idx = NULL, *top_sc = NULL;
-      if (topk > 0) {
-        top_idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)nq * (size_t)topk);
-        top_sc = (int32_t *)malloc(sizeof(int32_t) * (size_t)nq * (size_t)topk);
-        if (!top_idx || !top_sc) { fprintf(stderr, "malloc failed\n"); exit(1); }
-        if (sats_search_topk(sr[0], topk, top_idx, top_sc) != SATS_OK) die("ERROR selecting top hits");
+      /* hits-only modes: hcap rows per query come back from the device instead of one score per database entry */
+      const int hits_only = topk > 0 || zcut;
+      const int hcap = topk > 0 ? topk : (n > 0 ? n : 1);
+      int32_t *top_idx = NULL, *top_sc = NULL, *top_n = NULL;
+      if (hits_only) {
+        top_idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)nq * (size_t)hcap);
+        top_sc = (int32_t *)malloc(sizeof(int32_t) * (size_t)nq * (size_t)hcap);
+        top_n = (int32_t *)malloc(sizeof(int32_t) * (size_t)nq);
+        if (!top_idx || !top_sc || !top_n) { fprintf(stderr, "malloc failed\n"); exit(1); }
+        if (topk > 0) { if (sats_search_topk(sr[0], topk, top_idx, top_sc) != SATS_OK) die("ERROR selecting top hits"); }
+        else if (sats_search_hits(sr[0], zmin, hcap, top_n, top_idx, top_sc) != SATS_OK) die("ERROR selecting significant hits");
       } else {
         for (int g = 0; g < ngpus; g++)
           if (sats_search_collect(sr[g], scores, maps) != SATS_OK) die("ERROR collecting results");
@@ -234,24 +244,24 @@ int main(int argc, char *argv[])
       double ms = now_ms() - t1;
       fprintf(stderr, "GPU execution time %f ms (%d queries x %d entries, %s pool)\n", ms, nq, n, pass ? "large" : "small");
       fprintf(stderr, "%f million iterations/sec\n", ((double)nq * n * ((double)maxstart * SATS_MAXITER) / (ms / 1000)) / 1.0e6);
-      for (int q = 0; q < nq && topk > 0; q++) {
+      for (int q = 0; q < nq && hits_only; q++) {
         /* hits only: scatter the selected scores into this query's row and print them in rank order */
         int32_t *sc = scores + (size_t)q * dbsize;
         int nhit = 0;
-        while (nhit < topk && top_idx[(size_t)q * topk + nhit] >= 0) { sc[top_idx[(size_t)q * topk + nhit]] = top_sc[(size_t)q * topk + nhit]; nhit++; }
+        while (nhit < hcap && top_idx[(size_t)q * hcap + nhit] >= 0) { sc[top_idx[(size_t)q * hcap + nhit]] = top_sc[(size_t)q * hcap + nhit]; nhit++; }
         size_t need = sats_format_block(out, outcap, sats_db_name(queries, q0 + q), sats_db_order(queries, q0 + q), dbfile,
-                                        lorder, 0, db, top_idx + (size_t)q * topk, nhit, sc, NULL);
+                                        lorder, 0, db, top_idx + (size_t)q * hcap, nhit, sc, NULL);
         if (need >= outcap) {
           outcap = need + 1;
           out = (char *)realloc(out, outcap);
           if (!out) { fprintf(stderr, "malloc failed\n"); exit(1); }
           sats_format_block(out, outcap, sats_db_name(queries, q0 + q), sats_db_order(queries, q0 + q), dbfile, lorder, 0, db,
-                            top_idx + (size_t)q * topk, nhit, sc, NULL);
+                            top_idx + (size_t)q * hcap, nhit, sc, NULL);
         }
         fwrite(out, 1, need, stdout);
       }
-      free(top_idx); free(top_sc);
-      for (int q = 0; q < nq && topk == 0; q++) {
+      free(top_idx); free(top_sc); free(top_n);
+      for (int q = 0; q < nq && !hits_only; q++) {
         const int32_t *sc = scores + (size_t)q * dbsize;
         const int32_t *mp = lsoln ? maps + (size_t)q * dbsize * SATS_MAP_STRIDE : NULL;
         size_t need = sats_format_block(out, outcap, sats_db_name(queries, q0 + q), sats_db_order(queries, q0 + q),

@@ -76,6 +76,8 @@ struct sats_searcher {
   size_t score_cap = 0, map_cap = 0;
   int last_q = 0, last_lsoln = 0;
   int32_t *d_topk = nullptr, *h_topk = nullptr; size_t topk_cap = 0;
+  int32_t *d_sorted_order = nullptr;      // order of every resident entry, device order (for sats_search_hits)
+  int32_t *d_hits = nullptr, *h_hits = nullptr; size_t hits_cap = 0;
   long long launches = 0;
   bool attr_done = false;
 };
@@ -179,9 +181,11 @@ extern "C" int sats_searcher_create(const sats_db *db, int device, int shard_ran
   CKF(cudaMalloc(&s->d_pool_list, std::max<size_t>(1, local.size()) * 4));
   CKF(cudaMalloc(&s->d_xw_blocks, SATS_REF_GRID_BLOCKS * 4));
   CKF(cudaMemcpy(s->d_blobs, blobs.data(), blobs.size(), cudaMemcpyHostToDevice));
+  CKF(cudaMalloc(&s->d_sorted_order, std::max<size_t>(1, local.size()) * 4));
   if (!local.empty()) {
     CKF(cudaMemcpy(s->d_blob_off, off.data(), local.size() * 8, cudaMemcpyHostToDevice));
     CKF(cudaMemcpy(s->d_blob_bytes, bytes.data(), local.size() * 4, cudaMemcpyHostToDevice));
+    CKF(cudaMemcpy(s->d_sorted_order, s->sorted_order.data(), local.size() * 4, cudaMemcpyHostToDevice));
   }
   // Metropolis thresholds and temperatures exactly as the reference's host path evaluates them
   std::vector<float> temps(SATS_K_MOVES), tab((size_t)SATS_K_MOVES * (SATS_K_DCLAMP + 1));
@@ -208,6 +212,7 @@ extern "C" void sats_searcher_free(sats_searcher *s)
   cudaFree(s->d_blobs); cudaFree(s->d_blob_off); cudaFree(s->d_blob_bytes); cudaFree(s->d_accept); cudaFree(s->d_xw);
   cudaFree(s->d_pool_list); cudaFree(s->d_xw_blocks); cudaFree(s->d_counters); cudaFree(s->d_qblobs); cudaFree(s->d_qoff); cudaFree(s->d_qbytes);
   cudaFree(s->d_scores); cudaFree(s->d_maps); cudaFree(s->d_topk); cudaFreeHost(s->h_topk);
+  cudaFree(s->d_sorted_order); cudaFree(s->d_hits); cudaFreeHost(s->h_hits);
   cudaFreeHost(s->h_qstage); cudaFreeHost(s->h_scores); cudaFreeHost(s->h_maps);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
@@ -420,7 +425,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
         const int n1 = s->q_n1[q];
         k.q_first = q;
         k.sm_query_bytes = words_for(n1) > 2 ? SATS_K_QUERY_HDR : (int)s->q_bytes[q];
-        k.sm_mapwords = words_for(n1) > 2 ? (n1 + 3) / 4 : ((n1 + 3) & ~3);
+        k.sm_mapwords = words_for(n1) > 2 ? (n1 + 3) / 4 : n1;
         k.sm_bmapwords = pp->lsoln ? (n1 + 3) / 4 : 0;
         k.sm_team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * k.tw * 4 + 64);
         size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + k.sm_nan_bytes + k.sm_team_bytes;
@@ -453,7 +458,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
         for (int q = q0; q < q1; q++) { n1max = std::max(n1max, s->q_n1[q]); qbmax = std::max(qbmax, s->q_bytes[q]); }
         k.q_first = q0;
         k.sm_query_bytes = w1 > 2 ? SATS_K_QUERY_HDR : (int)qbmax;
-        k.sm_mapwords = w1 > 2 ? (n1max + 3) / 4 : ((n1max + 3) & ~3);     // whole groups of four: map_save reads them so
+        k.sm_mapwords = w1 > 2 ? (n1max + 3) / 4 : n1max;
         k.sm_bmapwords = pp->lsoln ? (n1max + 3) / 4 : 0;
         int b0 = r0;
         while (b0 < r1) {
@@ -698,6 +703,98 @@ extern "C" int sats_search_topk(sats_searcher *s, int k, int32_t *index_out, int
         index_out[(size_t)q * k + i] = -1;
         score_out[(size_t)q * k + i] = INT_MIN;
       }
+    }
+  }
+  return SATS_OK;
+}
+
+// ---- device-side significance cut ---------------------------------------------------------------------
+// One CTA per query slot.  thr[q][n2] is the smallest raw score whose Gumbel z-score reaches the cut for a structure of
+// order n2 (built on the host with the very functions the result printer uses, so the cut is exact).  Ordered compaction:
+// thread t owns a contiguous chunk of the device-ordered entries, a block scan places its hits; the CTA then reserves a
+// contiguous range of the shared pair buffer with one atomicAdd, so that only the hits have to travel to the host.
+__global__ void __launch_bounds__(SATS_TOPK_THREADS)
+sats_hits_kernel(const int32_t *scores, int stride, int count, const int32_t *orders, const int32_t *thr, int cap,
+                 int32_t *out_n, int32_t *out_base, int *cursor, int2 *pairs)
+{
+  __shared__ int scratch[SATS_TOPK_THREADS];
+  __shared__ int s_thr[SATS_MAXDIM_EXT + 1];
+  __shared__ int s_base;
+  const int q = blockIdx.x, t = threadIdx.x;
+  const int32_t *row = scores + (size_t)q * stride;
+  const int32_t none = (int32_t)0x80808080;
+  for (int n = t; n <= SATS_MAXDIM_EXT; n += SATS_TOPK_THREADS) s_thr[n] = thr[(size_t)q * (SATS_MAXDIM_EXT + 1) + n];
+  __syncthreads();
+  const int chunk = (count + SATS_TOPK_THREADS - 1) / SATS_TOPK_THREADS;
+  const int lo = min(count, t * chunk), hi = min(count, lo + chunk);
+  int mine = 0;
+  for (int e = lo; e < hi; e++) { int v = row[e]; mine += v != none && v >= s_thr[orders[e]]; }
+  int total;
+  int w = block_exclusive_scan(mine, scratch, &total);
+  if (t == 0) {
+    out_n[q] = total;
+    s_base = atomicAdd(cursor, min(total, cap));
+    out_base[q] = s_base;
+  }
+  __syncthreads();
+  int2 *dst = pairs + s_base;
+  for (int e = lo; e < hi && w < cap; e++) {
+    int v = row[e];
+    if (v != none && v >= s_thr[orders[e]]) dst[w++] = make_int2(e, v);
+  }
+}
+
+extern "C" int sats_search_hits(sats_searcher *s, double z_min, int cap, int32_t *count_out, int32_t *index_out, int32_t *score_out)
+{
+  if (!s || !count_out || !index_out || !score_out || cap < 1) return sats_fail(SATS_ERR_ARG, "sats_search_hits: bad argument");
+  if (s->last_q < 1) return sats_fail(SATS_ERR_ARG, "sats_search_hits: no search has been launched");
+  if (!(z_min == z_min)) return sats_fail(SATS_ERR_ARG, "sats_search_hits: z_min is NaN");
+  CK(cudaSetDevice(s->device));
+  const int D = (int)s->sorted_orig.size(), Q = s->last_q, T = SATS_MAXDIM_EXT + 1;
+  cap = std::min(cap, std::max(1, D));
+  // z is a non-decreasing step function of the raw score for fixed sizes (norm2 = 2 score / (n1 + n2), truncated to int
+  // at the z_gumbel call like the reference does): bisect for the first score that passes.  |score| <= 2 C(111, 2) = 12210.
+  const int kLo = -16384, kHi = 16384;
+  std::vector<int32_t> thr((size_t)Q * T);
+  for (int q = 0; q < Q; q++)
+    for (int n2 = 0; n2 < T; n2++) {
+      auto pass = [&](int sc) { return sats_z_gumbel((int)sats_norm2(sc, s->q_n1[q], n2), sats_gumbel_a, sats_gumbel_b) >= z_min; };
+      int lo = kLo, hi = kHi;
+      if (n2 == 0 || !pass(hi)) { thr[(size_t)q * T + n2] = INT_MAX; continue; }
+      while (lo < hi) { int mid = lo + (hi - lo) / 2; if (pass(mid)) hi = mid; else lo = mid + 1; }
+      thr[(size_t)q * T + n2] = lo;
+    }
+  // device / pinned buffer: [Q counts][Q bases][cursor][pad][thresholds Q x T][pairs: int2 x Q x cap]
+  const size_t head = 2 * (size_t)Q + 2, pair_off = (head + thr.size() + 1) & ~(size_t)1, words = pair_off + 2 * (size_t)Q * cap;
+  if (words > s->hits_cap) {
+    cudaFree(s->d_hits); cudaFreeHost(s->h_hits);
+    s->d_hits = nullptr; s->h_hits = nullptr; s->hits_cap = 0;
+    CK(cudaMalloc(&s->d_hits, words * 4));
+    CK(cudaMallocHost(&s->h_hits, words * 4));
+    s->hits_cap = words;
+  }
+  memset(s->h_hits, 0, head * 4);
+  memcpy(s->h_hits + head, thr.data(), thr.size() * 4);
+  CK(cudaMemcpyAsync(s->d_hits, s->h_hits, (head + thr.size()) * 4, cudaMemcpyHostToDevice, s->stream));
+  sats_hits_kernel<<<Q, SATS_TOPK_THREADS, 0, s->stream>>>(s->d_scores, std::max(1, D), D, s->d_sorted_order, s->d_hits + head, cap,
+                                                           s->d_hits, s->d_hits + Q, reinterpret_cast<int *>(s->d_hits + 2 * Q),
+                                                           reinterpret_cast<int2 *>(s->d_hits + pair_off));
+  CK(cudaGetLastError());
+  s->launches++;
+  CK(cudaMemcpyAsync(s->h_hits, s->d_hits, head * 4, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  const int32_t *h_n = s->h_hits, *h_base = s->h_hits + Q;
+  const size_t kept = (size_t)s->h_hits[2 * Q];                       // hits actually stored, all queries together
+  if (kept) CK(cudaMemcpyAsync(s->h_hits + pair_off, s->d_hits + pair_off, kept * 8, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  const int32_t *h_pairs = s->h_hits + pair_off;
+  for (int q = 0; q < Q; q++) {
+    count_out[q] = h_n[q];
+    const int got = std::min(h_n[q], cap);
+    const int32_t *pr = h_pairs + 2 * (size_t)h_base[q];
+    for (int i = 0; i < cap; i++) {
+      index_out[(size_t)q * cap + i] = i < got ? s->sorted_orig[pr[2 * i]] : -1;
+      score_out[(size_t)q * cap + i] = i < got ? pr[2 * i + 1] : INT_MIN;
     }
   }
   return SATS_OK;

@@ -38,7 +38,7 @@ struct SatsKParams {
   int sm_query_bytes;              // room for the largest query blob of this launch
   int sm_entry_bytes;              // room for the largest entry blob of this launch
   int sm_nan_bytes;                // room for one row of NaN-distance cells (8 B x largest entry order of this launch)
-  int sm_mapwords;                 // 32-bit words per live chain map: n1max rounded up to 4 (queries of <= 64 SSEs) or ceil(n1max / 4)
+  int sm_mapwords;                 // 32-bit words per live chain map: n1max (queries of <= 64 SSEs) or ceil(n1max / 4)
   int sm_bmapwords;                // 32-bit words per best map: ceil(n1max / 4) with lsoln, else 0
   int sm_team_bytes;               // total per team
   // search parameters

@@ -219,6 +219,14 @@ int sats_search_collect(sats_searcher *s, int32_t *scores, int32_t *maps);
  * file order (the device order).  index_out receives ORIGINAL db indices (-1 padding), score_out the raw scores
  * (INT32_MIN padding).  A sharded search returns each shard's local top-k; merge the shards on the host.          */
 int sats_search_topk(sats_searcher *s, int k, int32_t *index_out, int32_t *score_out);
+/* after sats_search_launch(), the significance cut ON THE DEVICE: every entry whose Gumbel z-score (the
+ * fourth output column, cudaSaTabsearch.cu:447-450) is >= z_min -- equivalently whose p-value is <= sats_pv_gumbel(z_min).
+ * The host turns the cut into one integer score threshold per (query, structure order) with the same functions the result
+ * printer uses (z is a non-decreasing step function of the raw score for fixed sizes), so the selection is exact; the
+ * device compares and compacts, and only the hits are copied back.  count_out[q] = number of hits of query slot q (it may
+ * exceed cap: the first cap hits are returned); index_out / score_out: rows of cap, hits in device order (decreasing
+ * structure order, then file order), ORIGINAL db indices, -1 / INT32_MIN padding.  Sharded search: one call per shard.  */
+int sats_search_hits(sats_searcher *s, double z_min, int cap, int32_t *count_out, int32_t *index_out, int32_t *score_out);
 int sats_searcher_sync(sats_searcher *s);
 /* kernels launched by this searcher since creation (for the bench's gpu_launches claim)          */
 long long sats_searcher_launch_count(const sats_searcher *s);

@@ -123,3 +123,26 @@ def test_cli_top_hits_only(tmp_path, fixtures):
     assert tscores[-1] >= sorted((int(r.split()[1]) for r in frows), reverse=True)[24]
     blocks = S.parse_results(top.stdout)
     assert len(blocks) == 1 and blocks[0]["query"] == "D2PHLB1" and len(blocks[0]["names"]) == 25
+
+
+def test_cli_significant_hits_only(tmp_path, fixtures):
+    """-z Z prints exactly the rows of the full run whose z-score column is >= Z (selected on the device)."""
+    ents = fixtures["small586"]
+    qs = [fixtures["queries_by_name"][n] for n in ("D2PHLB1", "D1UBIA_")]
+    write_ascii_db(tmp_path / "db.ascii", ents)
+    write_query_input(tmp_path / "q.input", "db.ascii", True, False, qs)
+    full = run([CLI, "-r", 128], tmp_path / "q.input", tmp_path)
+    cut = run([CLI, "-r", 128, "-z", "0.75"], tmp_path / "q.input", tmp_path)
+    assert full.returncode == 0 and cut.returncode == 0, cut.stderr.decode()[-1000:]
+    fb, cb = S.parse_results(full.stdout), S.parse_results(cut.stdout)
+    assert len(fb) == len(cb) == 2
+    total = 0
+    for f, c in zip(fb, cb):
+        assert f["query"] == c["query"]
+        want = {(n, s) for n, s, z in zip(f["names"], f["scores"], f["z"]) if z >= 0.75}
+        assert {(n, s) for n, s in zip(c["names"], c["scores"])} == want and len(c["names"]) == len(want)
+        assert all(z >= 0.75 for z in c["z"])
+        total += len(want)
+    assert 0 < total < 2 * len(ents)
+    bad = run([CLI, "-r", 8, "-z", "1", "-k", "3"], tmp_path / "q.input", tmp_path)
+    assert bad.returncode == 1 and b"cannot be combined" in bad.stderr

@@ -179,3 +179,31 @@ def test_device_topk_matches_host_selection(base, fixtures):
     idx, sc = small.topk(64)
     assert (idx[0, :50] >= 0).all() and (idx[0, 50:] == -1).all() and sorted(idx[0, :50].tolist()) == list(range(50))
     sr.close(); small.close()
+
+
+def test_device_significance_cut_matches_printed_z_scores(base, fixtures):
+    """sats_search_hits keeps exactly the entries whose z-score -- computed the way the result printer does
+    (norm2 truncated to int at the z_gumbel call, _refio.stats) -- reaches the cut; order = device order; counts beyond the
+    capacity are still reported."""
+    from _refio import stats
+    db = base.bootstrap(6000, 21, True)
+    qs = as_db([fixtures["queries_by_name"][n] for n in ("D1UBIA_", "D2PHLB1", "d1twfa_")] + structures_of(db, [17, 5999]))
+    sr = S.Searcher(db, 0)
+    sr.upload(qs)
+    sr.launch(S.default_params(lorder=1, lsoln=0, restarts=64, seed=5))
+    full, _ = sr.collect()
+    orders = db.orders()
+    qn = qs.orders()
+    devorder = np.argsort(-orders, kind="stable")
+    for z_min, cap in ((-0.4, 6000), (1.0, 6000), (2.5, 6000), (100.0, 8), (-1e9, 100)):
+        cnt, idx, sc = sr.hits(z_min, cap)
+        for q in range(len(qs)):
+            z = np.array([stats(int(full[q, e]), int(qn[q]), int(orders[e]))[1] for e in devorder])
+            want = devorder[z >= z_min]
+            assert cnt[q] == len(want), (z_min, q, cnt[q], len(want))
+            got = idx[q][idx[q] >= 0]
+            assert got.tolist() == want[:cap].tolist(), (z_min, q)
+            assert sc[q, :len(got)].tolist() == full[q][got].tolist()
+            assert (idx[q, len(got):] == -1).all()
+    assert cnt.min() == 6000                                   # the last cut (z >= -1e9) keeps everything
+    sr.close()
