@@ -3,6 +3,8 @@
 // kernel launches: db upload cudaSaTabsearch.cu:924-967, copyQueryToConstantMemory :486-558, init_rng :258-264
 // and :896-922, the launches :1042/:1223 and the result copies :1075-1087.
 #include <algorithm>
+#include <array>
+#include <map>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -63,6 +65,7 @@ struct sats_searcher {
   int32_t *d_pool_list = nullptr;
   int32_t *d_xw_blocks = nullptr;
   int num_sms = 148;
+  std::map<std::array<int, 7>, std::array<int, 4>> launch_cfg;   // launch shape per (kernel variant, shared-memory sizes)
   int *d_counters = nullptr; size_t counter_cap = 0;   // one work counter per (bucket launch, query) of a search
   // queries
   uint8_t *d_qblobs = nullptr; size_t qblob_cap = 0;
@@ -474,19 +477,29 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
           // team width (threads sharing one entry; results do not depend on it) and teams per CTA: whatever keeps the
           // most warps resident per SM; a narrower team only when it buys strictly more
           int best_teams = 0, best_warps = -1, best_tw = 0, best_team_bytes = 0, best_ctas = 0;
-          for (int tw = tw_max; tw >= 32; tw >>= 1) {
-            if (tw & 31) continue;             // 96 -> 48: not a whole number of warps
-            const int team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * tw * 4 + 64);
-            int teams_max = SATS_K_MAXTHREADS / tw;
-            if (const char *e = getenv("SATS_TEAMS")) teams_max = std::max(1, std::min(teams_max, atoi(e)));
-            for (int teams = teams_max; teams >= 1; teams--) {
-              size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + k.sm_nan_bytes + (size_t)teams * team_bytes;
-              if (smem > (size_t)kMaxSmem) continue;
-              int ctas = 0;
-              CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, fn, teams * tw, smem));
-              int warps = ctas * teams * tw / 32;
-              if (warps > best_warps) { best_warps = warps; best_teams = teams; best_tw = tw; best_team_bytes = team_bytes; best_ctas = ctas; }
+          // the choice depends only on the kernel variant and the shared-memory sizes: remember it (the occupancy queries
+          // below would otherwise cost a few hundred microseconds of host time per search)
+          const std::array<int, 7> cfg_key = {w1, words_for(n2max) * 4 + (pp->lorder != 0) * 2 + (pp->lsoln != 0), k.sm_query_bytes,
+                                              k.sm_entry_bytes, k.sm_mapwords, k.sm_bmapwords, tw_max};
+          auto hit = s->launch_cfg.find(cfg_key);
+          if (hit != s->launch_cfg.end()) {
+            best_tw = hit->second[0]; best_teams = hit->second[1]; best_team_bytes = hit->second[2]; best_ctas = hit->second[3];
+          } else {
+            for (int tw = tw_max; tw >= 32; tw >>= 1) {
+              if (tw & 31) continue;             // 96 -> 48: not a whole number of warps
+              const int team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * tw * 4 + 64);
+              int teams_max = SATS_K_MAXTHREADS / tw;
+              if (const char *e = getenv("SATS_TEAMS")) teams_max = std::max(1, std::min(teams_max, atoi(e)));
+              for (int teams = teams_max; teams >= 1; teams--) {
+                size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + k.sm_nan_bytes + (size_t)teams * team_bytes;
+                if (smem > (size_t)kMaxSmem) continue;
+                int ctas = 0;
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, fn, teams * tw, smem));
+                int warps = ctas * teams * tw / 32;
+                if (warps > best_warps) { best_warps = warps; best_teams = teams; best_tw = tw; best_team_bytes = team_bytes; best_ctas = ctas; }
+              }
             }
+            if (best_teams) s->launch_cfg[cfg_key] = {best_tw, best_teams, best_team_bytes, best_ctas};
           }
           if (best_teams == 0) return sats_fail(SATS_ERR_ARG, "query order %d x entry order %d does not fit in shared memory", n1max, n2max);
           const int tw = best_tw;
