@@ -105,10 +105,10 @@ static void fill_cells(const sats_db *db, int e, uint8_t *cells)
   for (int i = 0; i < n; i++)
     for (int j = 0; j < n; j++) {
       float d = db->dist(e, i, j);
-      // one-hot letters (zeta() in sats_kernel.cuh counts equal letters with AND + POPC); the diagonal holds the SSE
-      // type and is never scored
+      // (first letter << 4) | second letter, letters 0..4: the XOR of two codes indexes the kernel's zeta table
+      // (gated() in sats_kernel.cuh); the diagonal holds the SSE type and is never scored
       const uint32_t raw = db->code(e, i, j);
-      uint32_t code = (1u << std::min(raw >> 4, 4u)) | (256u << std::min(raw & 15u, 4u));
+      uint32_t code = (std::min(raw >> 4, 4u) << 4) | std::min(raw & 15u, 4u);
       memcpy(cells + 8 * ((size_t)i * n + j), &d, 4);
       memcpy(cells + 8 * ((size_t)i * n + j) + 4, &code, 4);
     }
@@ -431,7 +431,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
         k.sm_mapwords = words_for(n1) > 2 ? (n1 + 3) / 4 : n1;
         k.sm_bmapwords = pp->lsoln ? (n1 + 3) / 4 : 0;
         k.sm_team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * k.tw * 4 + 64);
-        size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + k.sm_nan_bytes + k.sm_team_bytes;
+        size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + k.sm_nan_bytes + SATS_K_ZTAB_BYTES + k.sm_team_bytes;
         if (smem > (size_t)kMaxSmem) return sats_fail(SATS_ERR_ARG, "query %d x entry order %d needs %zu B of shared memory", q, n2max, smem);
         kernel_fn fn = pick_kernel(words_for(n1), words_for(n2max), pp->lorder != 0, true, pp->lsoln != 0);
         fn<<<dim3((unsigned)blocks.size(), 1), k.tw, smem, s->stream>>>(k);
@@ -491,7 +491,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
               int teams_max = SATS_K_MAXTHREADS / tw;
               if (const char *e = getenv("SATS_TEAMS")) teams_max = std::max(1, std::min(teams_max, atoi(e)));
               for (int teams = teams_max; teams >= 1; teams--) {
-                size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + k.sm_nan_bytes + (size_t)teams * team_bytes;
+                size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + k.sm_nan_bytes + SATS_K_ZTAB_BYTES + (size_t)teams * team_bytes;
                 if (smem > (size_t)kMaxSmem) continue;
                 int ctas = 0;
                 CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, fn, teams * tw, smem));
@@ -507,7 +507,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
           k.teams = best_teams;
           k.sm_team_bytes = best_team_bytes;
           k.item_first = b0; k.item_count = b1 - b0;
-          size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + k.sm_nan_bytes + (size_t)k.teams * k.sm_team_bytes;
+          size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + k.sm_nan_bytes + SATS_K_ZTAB_BYTES + (size_t)k.teams * k.sm_team_bytes;
           // persistent teams: no more CTAs than fit on the device at once (per query); each team keeps claiming entries
           k.counters = s->d_counters + counter_base;
           counter_base += (size_t)(q1 - q0);

@@ -203,12 +203,18 @@ struct Xorwow {
 };
 
 // ------------------------------------------------------------------------------------------------ scoring
-// Tableau codes are stored one-hot in the device cells (first letter -> bit 0..4, second letter -> bit 8..12, see
-// sats_device.cu:fill_cells), so the number of equal letters is one AND + POPC.
-__device__ __forceinline__ int zeta(uint32_t a, uint32_t b)
+// tscord (kernel.cu:306-332) as a 128-byte table in shared memory.  A device cell carries its tableau code as
+// (first letter << 4) | second letter (letters 0..4), so q.code ^ e.code has a zero high field iff the first letters agree
+// and a zero low field iff the second letters agree, and zeta = table[q.code ^ e.code].  The table is 128-byte aligned and
+// exactly 32 words long: every word sits in its own bank, so lookups never conflict, and its address can be OR-ed into the
+// staged query cells once per CTA -- then zeta costs one LOP3 and one LDS.S8 per operand and nothing on the XU pipe
+// (AND + POPC + select on one-hot codes, the previous form, kept that pipe the second busiest).
+__device__ __forceinline__ void fill_zeta_table(int8_t *tab, int tid, int nthreads)
 {
-  const int hits = __popc(a & b);
-  return hits ? hits : -2;
+  for (int x = tid; x < 128; x += nthreads) {
+    const int hits = ((x >> 4) == 0) + ((x & 15) == 0);
+    tab[x] = (int8_t)(hits ? hits : -2);
+  }
 }
 __device__ __forceinline__ uint2 lds64(uint32_t addr)
 {
@@ -216,10 +222,28 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr)
   asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
   return v;
 }
+// q.y = table address | query code (see above), e.y = entry code
 __device__ __forceinline__ int gated(uint2 q, uint2 e)
 {
+  int z;
+  asm("ld.shared.s8 %0, [%1];" : "=r"(z) : "r"(q.y ^ e.y) : "memory");
   float gap = fabsf(__uint_as_float(q.x) - __uint_as_float(e.x));
-  return gap <= 4.0f ? zeta(q.y, e.y) : 0;
+  return gap <= 4.0f ? z : 0;
+}
+// once per CTA, after the query blob has landed: OR the table address into the code word of every staged query cell
+template <int W1> __device__ __forceinline__ void stamp_query_cells(uint8_t *sq, int n1, uint32_t ztab)
+{
+  if (W1 <= 2) {
+    uint32_t *cell = reinterpret_cast<uint32_t *>(sq + SATS_K_QUERY_HDR);
+    for (int c = threadIdx.x; c < n1 * n1; c += blockDim.x) cell[2 * c + 1] |= ztab;
+  }
+  __syncthreads();
+}
+// a query cell read from global memory (queries of more than 64 SSEs) still lacks the table address
+template <bool PATCH> __device__ __forceinline__ uint2 with_table(uint2 q, uint32_t ztab)
+{
+  if (PATCH) q.y |= ztab;
+  return q;
 }
 
 // Per-team view of shared memory (shared-window byte addresses)
@@ -229,6 +253,7 @@ struct TeamView {
   const uint8_t *qtype;    // n1
   uint32_t ecell;          // n2 x n2
   uint32_t nanrow;         // one row of cells whose distance is NaN: stands in for the missing side of a move
+  uint32_t ztab;           // the zeta table (128-byte aligned)
   const uint32_t *tmask;   // [4][4] type -> 128-bit mask of entry SSEs of that type
   uint32_t smap;           // this lane's live map (Map<W1 <= 2>)
   uint32_t bmap;           // this lane's best map (Map<false>)
@@ -353,7 +378,7 @@ struct Chain {
           while (bk) {
             int k = 32 * wk + __ffs(bk) - 1;
             bk &= bk - 1u;
-            total += gated(W1 > 2 ? __ldg(qrow_g + k) : lds64(qrow + (uint32_t)k * 8u),
+            total += gated(W1 > 2 ? with_table<true>(__ldg(qrow_g + k), v.ztab) : lds64(qrow + (uint32_t)k * 8u),
                            lds64(erow + LiveMap::off8(v.smap, k, v.mstride)));
           }
         }
@@ -382,7 +407,7 @@ struct Chain {
         b &= bits_below(z);
         const int k = 32 * w + z;
         const uint32_t l8 = LiveMap::off8(v.smap, k, v.mstride);
-        const uint2 q = W1 > 2 ? __ldg(qrow_g + k) : lds64(qrow + (uint32_t)k * 8u);
+        const uint2 q = W1 > 2 ? with_table<true>(__ldg(qrow_g + k), v.ztab) : lds64(qrow + (uint32_t)k * 8u);
         const uint2 ef = lds64(frow + l8), et = lds64(trow + l8);
         d += gated(q, et) - gated(q, ef);
       }
@@ -548,6 +573,7 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
 
 // Shared-memory layout of a CTA:
 //   [0, 128)                    mbarriers: one for the query, one per team
+//   then 256 B                  the 128-byte zeta table at the first 128-byte aligned address
 //   then sm_query_bytes         query blob (header + SSE types only when W1 == 4)
 //   then sm_nan_bytes           one row of {NaN, 0} cells
 //   then per team: entry blob (sm_entry_bytes) | live maps (mapwords*tw*4) | best maps (bmapwords*tw*4) | 64 B reduce scratch
@@ -557,10 +583,12 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
   using namespace satsk;
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem);       // bar[0]: query (and XORWOW entries); bar[1 + team]: that team's entries
-  uint8_t *sq = smem + SATS_K_BAR_BYTES;
+  const uint32_t zpad = (0u - (smem_u32(smem) + SATS_K_BAR_BYTES)) & 127u;       // up to the next 128-byte aligned address
+  int8_t *sz = reinterpret_cast<int8_t *>(smem + SATS_K_BAR_BYTES + zpad);
+  uint8_t *sq = smem + SATS_K_BAR_BYTES + SATS_K_ZTAB_BYTES;
   uint2 *snan = reinterpret_cast<uint2 *>(sq + p.sm_query_bytes);
   const int team = threadIdx.x / p.tw, tl = threadIdx.x - team * p.tw;
-  uint8_t *steam = smem + SATS_K_BAR_BYTES + p.sm_query_bytes + p.sm_nan_bytes + (size_t)team * p.sm_team_bytes;
+  uint8_t *steam = smem + SATS_K_BAR_BYTES + SATS_K_ZTAB_BYTES + p.sm_query_bytes + p.sm_nan_bytes + (size_t)team * p.sm_team_bytes;
   uint8_t *se = steam;
   uint8_t *smaps = se + p.sm_entry_bytes;
   uint8_t *bmaps = smaps + p.sm_mapwords * p.tw * 4;
@@ -570,6 +598,7 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
   if (threadIdx.x == 0)
     for (int t = 0; t <= p.teams; t++) mbar_init(bar + t, 1);
   for (int c = threadIdx.x; c < (p.sm_nan_bytes >> 3); c += blockDim.x) snan[c] = make_uint2(0x7fc00000u, 0u);
+  fill_zeta_table(sz, threadIdx.x, blockDim.x);
   __syncthreads();
 
   TeamView v;
@@ -581,6 +610,7 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
   v.qcell_g = reinterpret_cast<const uint2 *>(p.qblobs + p.qblob_off[qi] + SATS_K_QUERY_HDR);
   v.qcell = smem_u32(sq + SATS_K_QUERY_HDR);
   v.nanrow = smem_u32(snan);
+  v.ztab = smem_u32(sz);
   v.tmask = reinterpret_cast<const uint32_t *>(se + 16);
   v.ecell = smem_u32(se + SATS_K_ENTRY_HDR);
   v.smap = smem_u32(smaps + tl * 4);
@@ -601,6 +631,7 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
     const int32_t *qh = reinterpret_cast<const int32_t *>(sq);
     const int32_t *eh = reinterpret_cast<const int32_t *>(se);
     v.n1 = qh[0];
+    stamp_query_cells<W1>(sq, v.n1, v.ztab);
     uint64_t *tbar = bar + 1 + team;
     volatile int *claim = reinterpret_cast<volatile int *>(red + 4);      // red[0..3]: arg-max scratch of the team's warps
     int *counter = p.counters + blockIdx.y;
@@ -639,6 +670,7 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
     phase ^= 1u;
     const int32_t *qh = reinterpret_cast<const int32_t *>(sq);
     v.n1 = qh[0];
+    stamp_query_cells<W1>(sq, v.n1, v.ztab);
     for (int pos = b; pos < p.pool_count; pos += SATS_REF_GRID_BLOCKS) {
       const int e = p.pool_list[pos];
       if (threadIdx.x == 0) {

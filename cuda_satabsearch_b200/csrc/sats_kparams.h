@@ -11,6 +11,7 @@
 #define SATS_K_ENTRY_HDR 80        // 16 B header + 4 types x 4 words of type masks
 #define SATS_K_QUERY_HDR 128       // 16 B header + 112 B of SSE types
 #define SATS_K_BAR_BYTES 128       // shared-memory header: 1 + teams mbarriers (teams <= 12)
+#define SATS_K_ZTAB_BYTES 256      // shared-memory room for the 128-byte zeta table at a 128-byte aligned address
 #define SATS_K_MAPROW 112          // bytes per (query, entry) row of the device map output
 
 struct SatsKParams {
