@@ -415,13 +415,13 @@ struct Chain {
     return d;
   }
 
-  // One Metropolis move (kernel.cu:1032-1191).  u1/u2/u3 are callables so that a sequential generator
-  // is advanced exactly when the reference would draw (u2 only with >= 2 candidates).
-  template <class U1, class U2, class U3>
+  // One Metropolis move (kernel.cu:1032-1191) on query SSE i = scaled_index(first uniform of the move, n1).  u2/u3 are
+  // callables so that a sequential generator is advanced exactly when the reference would draw (u2 only with >= 2
+  // candidates).
+  template <class U2, class U3>
   __device__ __forceinline__ void move(const TeamView &v, int m, const SatsKParams &p, int &best, int &best_tag, int tag,
-                                       U1 &&u1, U2 &&u2, U3 &&u3)
+                                       const int i, U2 &&u2, U3 &&u3)
   {
-    const int i = scaled_index(u1(), v.n1);
     const bool was_mapped = bit_test<W1>(mq, i);
     int lo, hi, from;
     if (LORDER) {
@@ -527,7 +527,7 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
     }
     if (XORWOW) {
       for (int m = 0; m < SATS_K_MOVES; m++)
-        ch.move(v, m, p, best, best_tag, tag, [&] { return xw.next(); }, [&] { return xw.next(); }, [&] { return xw.next(); });
+        ch.move(v, m, p, best, best_tag, tag, scaled_index(xw.next(), v.n1), [&] { return xw.next(); }, [&] { return xw.next(); });
     } else {
       // static draw positions: move m, slot s -> draw 3m + s; four moves consume three Philox blocks
       for (int g = 0; g < SATS_K_MOVES / 4; g++) {
@@ -536,10 +536,14 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
         philox4x32_10(3u * g + 1u, (uint32_t)r, entry_orig, query_index, p.seed_lo, p.seed_hi, b);
         philox4x32_10(3u * g + 2u, (uint32_t)r, entry_orig, query_index, p.seed_lo, p.seed_hi, c);
         const int m = 4 * g;
-        ch.move(v, m + 0, p, best, best_tag, tag, [&] { return unit_from_bits(a[0]); }, [&] { return unit_from_bits(a[1]); }, [&] { return unit_from_bits(a[2]); });
-        ch.move(v, m + 1, p, best, best_tag, tag, [&] { return unit_from_bits(a[3]); }, [&] { return unit_from_bits(b[0]); }, [&] { return unit_from_bits(b[1]); });
-        ch.move(v, m + 2, p, best, best_tag, tag, [&] { return unit_from_bits(b[2]); }, [&] { return unit_from_bits(b[3]); }, [&] { return unit_from_bits(c[0]); });
-        ch.move(v, m + 3, p, best, best_tag, tag, [&] { return unit_from_bits(c[1]); }, [&] { return unit_from_bits(c[2]); }, [&] { return unit_from_bits(c[3]); });
+        // the SSE picks depend on the uniforms only, not on the chains' state: four independent conversion chains
+        // (XU and FP64 pipes) issued together, off the critical path of the moves
+        const int i0 = scaled_index(unit_from_bits(a[0]), v.n1), i1 = scaled_index(unit_from_bits(a[3]), v.n1);
+        const int i2 = scaled_index(unit_from_bits(b[2]), v.n1), i3 = scaled_index(unit_from_bits(c[1]), v.n1);
+        ch.move(v, m + 0, p, best, best_tag, tag, i0, [&] { return unit_from_bits(a[1]); }, [&] { return unit_from_bits(a[2]); });
+        ch.move(v, m + 1, p, best, best_tag, tag, i1, [&] { return unit_from_bits(b[0]); }, [&] { return unit_from_bits(b[1]); });
+        ch.move(v, m + 2, p, best, best_tag, tag, i2, [&] { return unit_from_bits(b[3]); }, [&] { return unit_from_bits(c[0]); });
+        ch.move(v, m + 3, p, best, best_tag, tag, i3, [&] { return unit_from_bits(c[2]); }, [&] { return unit_from_bits(c[3]); });
       }
     }
     if (LSOLN) ch.finish_best_map(v);
