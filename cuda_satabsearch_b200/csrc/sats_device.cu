@@ -65,7 +65,7 @@ struct sats_searcher {
   int32_t *d_pool_list = nullptr;
   int32_t *d_xw_blocks = nullptr;
   int num_sms = 148;
-  std::map<std::array<int, 7>, std::array<int, 4>> launch_cfg;   // launch shape per (kernel variant, shared-memory sizes)
+  std::map<std::array<int, 8>, std::array<int, 4>> launch_cfg;   // launch shape per (kernel variant, shared-memory sizes)
   int *d_counters = nullptr; size_t counter_cap = 0;   // one work counter per (bucket launch, query) of a search
   // queries
   uint8_t *d_qblobs = nullptr; size_t qblob_cap = 0;
@@ -430,7 +430,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
         k.sm_query_bytes = words_for(n1) > 2 ? SATS_K_QUERY_HDR : (int)s->q_bytes[q];
         k.sm_mapwords = words_for(n1) > 2 ? (n1 + 3) / 4 : n1;
         k.sm_bmapwords = pp->lsoln ? (n1 + 3) / 4 : 0;
-        k.sm_team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * k.tw * 4 + 64);
+        k.sm_team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * k.tw * 4 + 64 + (size_t)n1 * words_for(n2max) * 4);
         size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + k.sm_nan_bytes + SATS_K_ZTAB_BYTES + k.sm_team_bytes;
         if (smem > (size_t)kMaxSmem) return sats_fail(SATS_ERR_ARG, "query %d x entry order %d needs %zu B of shared memory", q, n2max, smem);
         kernel_fn fn = pick_kernel(words_for(n1), words_for(n2max), pp->lorder != 0, true, pp->lsoln != 0);
@@ -479,15 +479,15 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
           int best_teams = 0, best_warps = -1, best_tw = 0, best_team_bytes = 0, best_ctas = 0;
           // the choice depends only on the kernel variant and the shared-memory sizes: remember it (the occupancy queries
           // below would otherwise cost a few hundred microseconds of host time per search)
-          const std::array<int, 7> cfg_key = {w1, words_for(n2max) * 4 + (pp->lorder != 0) * 2 + (pp->lsoln != 0), k.sm_query_bytes,
-                                              k.sm_entry_bytes, k.sm_mapwords, k.sm_bmapwords, tw_max};
+          const std::array<int, 8> cfg_key = {w1, words_for(n2max) * 4 + (pp->lorder != 0) * 2 + (pp->lsoln != 0), k.sm_query_bytes,
+                                              k.sm_entry_bytes, k.sm_mapwords, k.sm_bmapwords, tw_max, n1max};
           auto hit = s->launch_cfg.find(cfg_key);
           if (hit != s->launch_cfg.end()) {
             best_tw = hit->second[0]; best_teams = hit->second[1]; best_team_bytes = hit->second[2]; best_ctas = hit->second[3];
           } else {
             for (int tw = tw_max; tw >= 32; tw >>= 1) {
               if (tw & 31) continue;             // 96 -> 48: not a whole number of warps
-              const int team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * tw * 4 + 64);
+              const int team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * tw * 4 + 64 + (size_t)n1max * words_for(n2max) * 4);
               int teams_max = SATS_K_MAXTHREADS / tw;
               if (const char *e = getenv("SATS_TEAMS")) teams_max = std::max(1, std::min(teams_max, atoi(e)));
               for (int teams = teams_max; teams >= 1; teams--) {

@@ -216,6 +216,12 @@ __device__ __forceinline__ void fill_zeta_table(int8_t *tab, int tid, int nthrea
     tab[x] = (int8_t)(hits ? hits : -2);
   }
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+  uint32_t v;
+  asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint2 lds64(uint32_t addr)
 {
   uint2 v;
@@ -255,6 +261,7 @@ struct TeamView {
   uint32_t nanrow;         // one row of cells whose distance is NaN: stands in for the missing side of a move
   uint32_t ztab;           // the zeta table (128-byte aligned)
   const uint32_t *tmask;   // [4][4] type -> 128-bit mask of entry SSEs of that type
+  uint32_t qmask;          // [n1][W2] per query SSE: the mask of entry SSEs of its type (built per entry, one load per move)
   uint32_t smap;           // this lane's live map (Map<W1 <= 2>)
   uint32_t bmap;           // this lane's best map (Map<false>)
   uint32_t mstride;        // tw * 4: consecutive lanes own consecutive banks, so lane-private accesses never conflict
@@ -343,10 +350,9 @@ struct Chain {
     for (int i = 0; i < v.n1; i++) {
       float u = draw(i);
       if (u < 0.5f) {
-        const uint32_t *tm = v.tmask + 4 * v.qtype[i];
         uint32_t cand[W2];
 #pragma unroll
-        for (int w = 0; w < W2; w++) cand[w] = tm[w];
+        for (int w = 0; w < W2; w++) cand[w] = lds32(v.qmask + (uint32_t)(i * W2 + w) * 4u);
         int j = low_at_or_above<W2>(cand, next_j);
         if (j < 0) break;
         LiveMap::put(v.smap, i, v.mstride, j);
@@ -438,12 +444,11 @@ struct Chain {
       from = was_mapped ? LiveMap::get(v.smap, i, v.mstride) : -1;
     }
     // randtypeind (kernel.cu:677-714): unoccupied entry SSEs of the right type inside [lo, hi)
-    const uint32_t *tm = v.tmask + 4 * v.qtype[i];
     uint32_t cand[W2];
     int ncand = 0;
 #pragma unroll
     for (int w = 0; w < W2; w++) {
-      cand[w] = tm[w] & ~md[w] & below(hi - 32 * w) & ~below(lo - 32 * w);
+      cand[w] = lds32(v.qmask + (uint32_t)(i * W2 + w) * 4u) & ~md[w] & below(hi - 32 * w) & ~below(lo - 32 * w);
       ncand += __popc(cand[w]);
     }
     int to = -1;
@@ -493,6 +498,13 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
                                              uint32_t entry_orig, uint32_t query_index, Xorwow &xw,
                                              int out_slot, int entry_sorted)
 {
+  // per query SSE, the entry SSEs of its type (the previous entry's users are past its closing barrier)
+  for (int k = tl; k < v.n1; k += p.tw) {
+    const uint32_t *tm = v.tmask + 4 * v.qtype[k];
+#pragma unroll
+    for (int w = 0; w < W2; w++) asm volatile("st.shared.b32 [%0], %1;" ::"r"(v.qmask + (uint32_t)(k * W2 + w) * 4u), "r"(tm[w]) : "memory");
+  }
+  team_sync(team, p.tw);
   Chain<W1, W2, LORDER, XORWOW, LSOLN> ch;
   int best = SATS_K_NEG_INIT;
   int best_tag = tl;                                  // XORWOW: thread id; Philox: restart index of the best chain
@@ -580,7 +592,7 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
 //   then 256 B                  the 128-byte zeta table at the first 128-byte aligned address
 //   then sm_query_bytes         query blob (header + SSE types only when W1 == 4)
 //   then sm_nan_bytes           one row of {NaN, 0} cells
-//   then per team: entry blob (sm_entry_bytes) | live maps (mapwords*tw*4) | best maps (bmapwords*tw*4) | 64 B reduce scratch
+//   then per team: entry blob (sm_entry_bytes) | live maps (mapwords*tw*4) | best maps (bmapwords*tw*4) | 64 B reduce scratch | qmask (n1 x W2 words)
 template <int W1, int W2, bool LORDER, bool XORWOW, bool LSOLN>
 __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anneal_kernel(const SatsKParams p)
 {
@@ -619,6 +631,7 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
   v.ecell = smem_u32(se + SATS_K_ENTRY_HDR);
   v.smap = smem_u32(smaps + tl * 4);
   v.bmap = smem_u32(bmaps + tl * 4);
+  v.qmask = smem_u32(red + 8);
   Xorwow xw;
 
   if (!XORWOW) {
