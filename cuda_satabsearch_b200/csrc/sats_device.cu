@@ -430,7 +430,8 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
         k.sm_query_bytes = words_for(n1) > 2 ? SATS_K_QUERY_HDR : (int)s->q_bytes[q];
         k.sm_mapwords = words_for(n1) > 2 ? (n1 + 3) / 4 : n1;
         k.sm_bmapwords = pp->lsoln ? (n1 + 3) / 4 : 0;
-        k.sm_team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * k.tw * 4 + 64 + (size_t)n1 * words_for(n2max) * 4);
+        k.sm_qmask_bytes = (int)round16((size_t)n1 * words_for(n2max) * 4);
+        k.sm_team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * k.tw * 4 + SATS_K_SCRATCH_BYTES + (size_t)(k.tw / 32) * k.sm_qmask_bytes);
         size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + k.sm_nan_bytes + SATS_K_ZTAB_BYTES + k.sm_team_bytes;
         if (smem > (size_t)kMaxSmem) return sats_fail(SATS_ERR_ARG, "query %d x entry order %d needs %zu B of shared memory", q, n2max, smem);
         kernel_fn fn = pick_kernel(words_for(n1), words_for(n2max), pp->lorder != 0, true, pp->lsoln != 0);
@@ -473,6 +474,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
           while (b1 < r1 && s->sorted_order[b1] > lowbound) b1++;
           k.sm_entry_bytes = (int)entry_blob_bytes(n2max);
           k.sm_nan_bytes = (int)round16(8 * (size_t)n2max);
+          k.sm_qmask_bytes = (int)round16((size_t)n1max * words_for(n2max) * 4);
           kernel_fn fn = pick_kernel(w1, words_for(n2max), pp->lorder != 0, false, pp->lsoln != 0);
           // team width (threads sharing one entry; results do not depend on it) and teams per CTA: whatever keeps the
           // most warps resident per SM; a narrower team only when it buys strictly more
@@ -487,7 +489,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
           } else {
             for (int tw = tw_max; tw >= 32; tw >>= 1) {
               if (tw & 31) continue;             // 96 -> 48: not a whole number of warps
-              const int team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * tw * 4 + 64 + (size_t)n1max * words_for(n2max) * 4);
+              const int team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * tw * 4 + SATS_K_SCRATCH_BYTES + (size_t)(tw / 32) * k.sm_qmask_bytes);
               int teams_max = SATS_K_MAXTHREADS / tw;
               if (const char *e = getenv("SATS_TEAMS")) teams_max = std::max(1, std::min(teams_max, atoi(e)));
               for (int teams = teams_max; teams >= 1; teams--) {

@@ -493,18 +493,21 @@ struct Chain {
 };
 
 // Runs every chain this thread owns for one (query, entry) pair, then the team arg-max and the output.
-template <int W1, int W2, bool LORDER, bool XORWOW, bool LSOLN>
+// `red` is this entry's arg-max scratch (the callers alternate between two, so that the one team barrier per entry is
+// enough); `before_barrier` runs on every thread after its chains and before that barrier, `after_barrier` right after it
+// (from then on nobody reads the entry blob any more: the persistent loop claims and fetches the next entry there).
+template <int W1, int W2, bool LORDER, bool XORWOW, bool LSOLN, class Before, class After>
 __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamView &v, int team, int tl, uint64_t *red,
                                              uint32_t entry_orig, uint32_t query_index, Xorwow &xw,
-                                             int out_slot, int entry_sorted)
+                                             int out_slot, int entry_sorted, Before &&before_barrier, After &&after_barrier)
 {
-  // per query SSE, the entry SSEs of its type (the previous entry's users are past its closing barrier)
-  for (int k = tl; k < v.n1; k += p.tw) {
+  // per query SSE, the entry SSEs of its type: every warp keeps its own copy, so a warp barrier is all it takes
+  for (int k = tl & 31; k < v.n1; k += 32) {
     const uint32_t *tm = v.tmask + 4 * v.qtype[k];
 #pragma unroll
     for (int w = 0; w < W2; w++) asm volatile("st.shared.b32 [%0], %1;" ::"r"(v.qmask + (uint32_t)(k * W2 + w) * 4u), "r"(tm[w]) : "memory");
   }
-  team_sync(team, p.tw);
+  __syncwarp();
   Chain<W1, W2, LORDER, XORWOW, LSOLN> ch;
   int best = SATS_K_NEG_INIT;
   int best_tag = tl;                                  // XORWOW: thread id; Philox: restart index of the best chain
@@ -567,7 +570,9 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
   unsigned wtag = __reduce_min_sync(full, best == wbest ? (unsigned)best_tag : 0xffffffffu);
   const int warp_in_team = tl >> 5, warps = p.tw >> 5;
   if ((tl & 31) == 0) red[warp_in_team] = ((uint64_t)(uint32_t)(wbest + 0x40000000) << 32) | (uint32_t)(~wtag);
+  before_barrier();
   team_sync(team, p.tw);
+  after_barrier();
   uint64_t key = red[0];
   for (int w = 1; w < warps; w++) key = red[w] > key ? red[w] : key;
   const int team_best = (int)(uint32_t)(key >> 32) - 0x40000000;
@@ -582,7 +587,6 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
       reinterpret_cast<uint32_t *>(row)[w] = x;
     }
   }
-  team_sync(team, p.tw);     // red[] and the entry buffer may be reused after this
 }
 
 }  // namespace satsk
@@ -592,7 +596,7 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
 //   then 256 B                  the 128-byte zeta table at the first 128-byte aligned address
 //   then sm_query_bytes         query blob (header + SSE types only when W1 == 4)
 //   then sm_nan_bytes           one row of {NaN, 0} cells
-//   then per team: entry blob (sm_entry_bytes) | live maps (mapwords*tw*4) | best maps (bmapwords*tw*4) | 64 B reduce scratch | qmask (n1 x W2 words)
+//   then per team: entry blob (sm_entry_bytes) | live maps (mapwords*tw*4) | best maps (bmapwords*tw*4) | 80 B scratch (2 arg-max buffers, 2 claim slots) | one qmask (n1 x W2 words) per warp
 template <int W1, int W2, bool LORDER, bool XORWOW, bool LSOLN>
 __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anneal_kernel(const SatsKParams p)
 {
@@ -631,7 +635,9 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
   v.ecell = smem_u32(se + SATS_K_ENTRY_HDR);
   v.smap = smem_u32(smaps + tl * 4);
   v.bmap = smem_u32(bmaps + tl * 4);
-  v.qmask = smem_u32(red + 8);
+  // team scratch: red[2][4] (two alternating arg-max buffers) | claim[2] | per-warp qmask copies
+  volatile int *claim = reinterpret_cast<volatile int *>(red + 8);
+  v.qmask = smem_u32(reinterpret_cast<uint8_t *>(red) + SATS_K_SCRATCH_BYTES + (tl >> 5) * p.sm_qmask_bytes);
   Xorwow xw;
 
   if (!XORWOW) {
@@ -650,27 +656,36 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
     v.n1 = qh[0];
     stamp_query_cells<W1>(sq, v.n1, v.ztab);
     uint64_t *tbar = bar + 1 + team;
-    volatile int *claim = reinterpret_cast<volatile int *>(red + 4);      // red[0..3]: arg-max scratch of the team's warps
     int *counter = p.counters + blockIdx.y;
-    uint32_t phase = 0;
-    for (;;) {
-      if (tl == 0) {
-        const int idx = atomicAdd(counter, 1);
-        *claim = idx;
-        if (idx < p.item_count) {
-          const int e = p.item_first + idx;
-          const uint32_t bytes = p.blob_bytes[e];
-          mbar_expect_tx(tbar, bytes);
-          tma_load_1d(se, p.blobs + p.blob_off[e], bytes, tbar);
-        }
+    // claim an entry (leader only): take the next list position, publish it in claim[slot]; fetch it if there is one
+    auto claim_next = [&](int slot) {
+      const int idx = atomicAdd(counter, 1);
+      claim[slot] = idx;
+      return idx;
+    };
+    auto fetch = [&](int idx) {
+      if (idx < p.item_count) {
+        const int e = p.item_first + idx;
+        const uint32_t bytes = p.blob_bytes[e];
+        mbar_expect_tx(tbar, bytes);
+        tma_load_1d(se, p.blobs + p.blob_off[e], bytes, tbar);
       }
-      team_sync(team, p.tw);
-      const int idx = *claim;
+    };
+    if (tl == 0) fetch(claim_next(0));
+    team_sync(team, p.tw);
+    uint32_t phase = 0;
+    // One team barrier per entry (the arg-max).  The leader takes the next list position once its own chains are done,
+    // before that barrier, so the barrier also publishes it; right after the barrier nobody needs the entry blob any more
+    // and the leader starts the next TMA copy, which then overlaps the arg-max and the output.
+    for (int par = 0;; par ^= 1) {
+      const int idx = claim[par];
       if (idx >= p.item_count) break;
       mbar_wait(tbar, phase);
       phase ^= 1u;
       v.n2 = eh[0];
-      anneal_entry<W1, W2, LORDER, false, LSOLN>(p, v, team, tl, red, (uint32_t)eh[1], (uint32_t)qh[1], xw, qi, p.item_first + idx);
+      anneal_entry<W1, W2, LORDER, false, LSOLN>(p, v, team, tl, red + 4 * par, (uint32_t)eh[1], (uint32_t)qh[1], xw, qi, p.item_first + idx,
+                                                 [&] { if (tl == 0) claim_next(par ^ 1); },
+                                                 [&] { if (tl == 0) fetch(claim[par ^ 1]); });
     }
   } else {
     // validation: this CTA is reference block b; one team of 128 threads; entries b, b+128, ... in pool order
@@ -698,7 +713,8 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
       phase ^= 1u;
       const int32_t *eh = reinterpret_cast<const int32_t *>(se);
       v.n2 = eh[0];
-      anneal_entry<W1, W2, LORDER, true, LSOLN>(p, v, 0, tl, red, (uint32_t)eh[1], (uint32_t)qh[1], xw, qi, e);
+      anneal_entry<W1, W2, LORDER, true, LSOLN>(p, v, 0, tl, red, (uint32_t)eh[1], (uint32_t)qh[1], xw, qi, e, [] {}, [] {});
+      __syncthreads();       // the entry buffer and the arg-max scratch are reused by the next entry
     }
     xw.store(st);
   }
