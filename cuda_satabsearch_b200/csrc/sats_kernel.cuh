@@ -434,11 +434,9 @@ struct Chain {
       int kp = top_at_or_below<W1>(mq, i);
       lo = kp >= 0 ? LiveMap::get(v.smap, kp, v.mstride) : v.n2;
       from = was_mapped ? lo : -1;
+      const int kn = low_at_or_above<W1>(mq, i + 1);            // -1 for the last query SSE: nothing above it
+      hi = kn >= 0 ? LiveMap::get(v.smap, kn, v.mstride) : -1;
       if (i == v.n1 - 1) hi = v.n2;
-      else {
-        int kn = low_at_or_above<W1>(mq, i + 1);
-        hi = kn >= 0 ? LiveMap::get(v.smap, kn, v.mstride) : -1;
-      }
     } else {
       lo = 0; hi = v.n2;
       from = was_mapped ? LiveMap::get(v.smap, i, v.mstride) : -1;
