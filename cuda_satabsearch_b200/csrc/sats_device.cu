@@ -41,6 +41,15 @@ __global__ void sats_xorwow_init_kernel(uint32_t *states, int n, unsigned long l
   for (int k = 0; k < 5; k++) o[1 + k] = st.v[k];
 }
 
+typedef sats_kernel_fn kernel_fn;
+// one kernel launch of a search, as planned on the host
+struct LaunchDesc {
+  kernel_fn fn;
+  unsigned grid_x, grid_y, threads;
+  size_t smem;
+  SatsKParams k;
+};
+
 struct sats_searcher {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -65,7 +74,12 @@ struct sats_searcher {
   int32_t *d_pool_list = nullptr;
   int32_t *d_xw_blocks = nullptr;
   int num_sms = 148;
-  std::map<std::array<int, 8>, std::array<int, 4>> launch_cfg;   // launch shape per (kernel variant, shared-memory sizes)
+  std::map<std::array<int, 8>, std::array<int, 4>> launch_cfg;
+  // the launches of the last production-mode search, captured as a CUDA graph (counter reset, fork to the side streams,
+  // one kernel per size bucket, join): an unchanged plan is replayed with a single cudaGraphLaunch
+  std::vector<LaunchDesc> graph_plan;
+  size_t graph_counters = 0;
+  cudaGraphExec_t graph_exec = nullptr;   // launch shape per (kernel variant, shared-memory sizes)
   int *d_counters = nullptr; size_t counter_cap = 0;   // one work counter per (bucket launch, query) of a search
   // queries
   uint8_t *d_qblobs = nullptr; size_t qblob_cap = 0;
@@ -85,7 +99,7 @@ struct sats_searcher {
   bool attr_done = false;
 };
 
-typedef sats_kernel_fn kernel_fn;
+
 static kernel_fn pick_kernel(int w1, int w2, bool lorder, bool xorwow, bool lsoln)
 {
   switch (w1) {
@@ -216,6 +230,7 @@ extern "C" void sats_searcher_free(sats_searcher *s)
   cudaFree(s->d_pool_list); cudaFree(s->d_xw_blocks); cudaFree(s->d_counters); cudaFree(s->d_qblobs); cudaFree(s->d_qoff); cudaFree(s->d_qbytes);
   cudaFree(s->d_scores); cudaFree(s->d_maps); cudaFree(s->d_topk); cudaFreeHost(s->h_topk);
   cudaFree(s->d_sorted_order); cudaFree(s->d_hits); cudaFreeHost(s->h_hits);
+  if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
   cudaFreeHost(s->h_qstage); cudaFreeHost(s->h_scores); cudaFreeHost(s->h_maps);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
@@ -446,13 +461,10 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
         CK(cudaMalloc(&s->d_counters, ncounters * sizeof(int)));
         s->counter_cap = ncounters;
       }
-      CK(cudaMemsetAsync(s->d_counters, 0, ncounters * sizeof(int), s->stream));
       size_t counter_base = 0;
+      std::vector<LaunchDesc> plan;
       int tw_max = std::min(128, ((pp->restarts + 31) / 32) * 32);
       if (const char *e = getenv("SATS_TW")) { int t = atoi(e); if (t == 32 || t == 64 || t == 128) tw_max = std::min(tw_max, t); }
-      CK(cudaEventRecord(s->fork, s->stream));
-      for (int i = 0; i < sats_searcher::kSide; i++) CK(cudaStreamWaitEvent(s->side[i], s->fork, 0));
-      int nlaunch = 0;
       // runs of consecutive queries with the same mask width share launches (grid.y)
       for (int q0 = 0; q0 < Q;) {
         int q1 = q0 + 1;
@@ -515,18 +527,55 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
           counter_base += (size_t)(q1 - q0);
           const int resident = std::max(1, best_ctas) * s->num_sms;
           dim3 grid((unsigned)std::min((k.item_count + k.teams - 1) / k.teams, resident), (unsigned)(q1 - q0));
-          fn<<<grid, k.teams * tw, smem, s->side[nlaunch % sats_searcher::kSide]>>>(k);
-          CK(cudaGetLastError());
-          s->launches++;
-          nlaunch++;
+          LaunchDesc ld;
+          memset(&ld, 0, sizeof ld);
+          ld.fn = fn; ld.grid_x = grid.x; ld.grid_y = grid.y; ld.threads = (unsigned)(k.teams * tw); ld.smem = smem; ld.k = k;
+          plan.push_back(ld);
           b0 = b1;
         }
         q0 = q1;
       }
-      for (int i = 0; i < sats_searcher::kSide; i++) {
-        CK(cudaEventRecord(s->side_done[i], s->side[i]));
-        CK(cudaStreamWaitEvent(s->stream, s->side_done[i], 0));
+      // enqueue: counter reset, fork, the bucket kernels round-robin over the side streams (so that the tail of one bucket
+      // overlaps the head of the next), join
+      auto enqueue = [&]() -> int {
+        CK(cudaMemsetAsync(s->d_counters, 0, ncounters * sizeof(int), s->stream));
+        CK(cudaEventRecord(s->fork, s->stream));
+        for (int i = 0; i < sats_searcher::kSide; i++) CK(cudaStreamWaitEvent(s->side[i], s->fork, 0));
+        for (size_t n = 0; n < plan.size(); n++) {
+          const LaunchDesc &ld = plan[n];
+          ld.fn<<<dim3(ld.grid_x, ld.grid_y), ld.threads, ld.smem, s->side[n % sats_searcher::kSide]>>>(ld.k);
+          CK(cudaGetLastError());
+        }
+        for (int i = 0; i < sats_searcher::kSide; i++) {
+          CK(cudaEventRecord(s->side_done[i], s->side[i]));
+          CK(cudaStreamWaitEvent(s->stream, s->side_done[i], 0));
+        }
+        return SATS_OK;
+      };
+      static const bool no_graph = getenv("SATS_NO_GRAPH") != nullptr;
+      if (no_graph) {
+        rc = enqueue();
+        if (rc) return rc;
+      } else {
+        const bool same = s->graph_exec && s->graph_counters == ncounters && s->graph_plan.size() == plan.size() &&
+                          (plan.empty() || memcmp(s->graph_plan.data(), plan.data(), plan.size() * sizeof(LaunchDesc)) == 0);
+        if (!same) {
+          if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+          cudaGraph_t graph = nullptr;
+          CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+          rc = enqueue();
+          cudaError_t ce = cudaStreamEndCapture(s->stream, &graph);
+          if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+          CK(ce);
+          ce = cudaGraphInstantiate(&s->graph_exec, graph, 0);
+          cudaGraphDestroy(graph);
+          CK(ce);
+          s->graph_plan = plan;
+          s->graph_counters = ncounters;
+        }
+        CK(cudaGraphLaunch(s->graph_exec, s->stream));
       }
+      s->launches += (long long)plan.size();
     }
   }
   if (elapsed_ms) {
