@@ -13,15 +13,16 @@
  * Differences, all deliberate: -c is refused (this build has no CPU search path); -q computes norm2 with the
  * query's own order like the reference's CPU branch (:366, :380) rather than the GPU branch's orders[qi]
  * (:996-998); the db file may also be a packed SATSDB1 cache.  Extra options:
- *   -g N      use N GPUs (cost-weighted shards of the size-sorted db; Philox mode only)
+ *   -g N      N cost-weighted shards of the size-sorted db, one per GPU (shards share devices when N exceeds the GPUs
+ *             present); Philox mode only
  *   -R mode   philox (default) | xorwow  -- xorwow = the reference GPU run's 128x128 cuRAND streams
  *   -A mode   table (default) | fast     -- Metropolis thresholds: host libm table | device fast-math
  *   -s seed   RNG seed (default 1234)
  *   -L        also search database structures of order 112..128 (the reference drops everything above 111)
  *   -k N      print only the N best-scoring structures of each (query, pool) block, best first (selected on the
- *             device with sats_search_topk, so only N rows per query leave the GPU); single GPU, LSOLN = F
+ *             device with sats_search_topk, so only N rows per query leave each GPU); LSOLN = F
  *   -z Z      print only the structures whose z-score (4th column) is >= Z, in database order of decreasing size
- *             (selected on the device with sats_search_hits); single GPU, LSOLN = F, not together with -k
+ *             (selected on the device with sats_search_hits); LSOLN = F, not together with -k
  */
 #include <getopt.h>
 #include <stdio.h>
@@ -44,6 +45,21 @@ static void die(const char *what)
 {
   fprintf(stderr, "%s: %s\n", what, sats_last_error());
   exit(1);
+}
+
+/* one selected row while the shards' hit lists are merged */
+typedef struct { int32_t index, score, order; } hit_t;
+static int by_device_order(const void *a, const void *b)
+{
+  const hit_t *x = (const hit_t *)a, *y = (const hit_t *)b;
+  if (x->order != y->order) return x->order > y->order ? -1 : 1;     /* larger structures first ... */
+  return (x->index > y->index) - (x->index < y->index);              /* ... then file order */
+}
+static int by_score_then_device_order(const void *a, const void *b)
+{
+  const hit_t *x = (const hit_t *)a, *y = (const hit_t *)b;
+  if (x->score != y->score) return x->score > y->score ? -1 : 1;
+  return by_device_order(a, b);
 }
 
 static void usage(const char *prog)
@@ -128,8 +144,8 @@ int main(int argc, char *argv[])
     fprintf(stderr, "ERROR: -R xorwow reproduces a single-GPU reference run; use -g 1\n");
     exit(1);
   }
-  if (topk < 0 || (topk > 0 && ngpus > 1)) { fprintf(stderr, "ERROR: -k needs a positive count and a single GPU\n"); exit(1); }
-  if (zcut && (ngpus > 1 || topk > 0)) { fprintf(stderr, "ERROR: -z needs a single GPU and cannot be combined with -k\n"); exit(1); }
+  if (topk < 0) { fprintf(stderr, "ERROR: -k needs a positive count\n"); exit(1); }
+  if (zcut && topk > 0) { fprintf(stderr, "ERROR: -z cannot be combined with -k\n"); exit(1); }
   fprintf(stderr, "MAXDIM = %d\n", max_order);
 
   size_t inlen = 0;
@@ -188,13 +204,13 @@ int main(int argc, char *argv[])
 
   int have = sats_device_count();
   if (have < 1) { fprintf(stderr, "ERROR: no CUDA device found (this build has no CPU search path)\n"); exit(1); }
-  if (ngpus > have) { fprintf(stderr, "ERROR: %d GPUs requested, %d present\n", ngpus, have); exit(1); }
+  if (ngpus > have) fprintf(stderr, "WARNING: %d shards requested, %d GPU(s) present: shards share devices\n", ngpus, have);
   fprintf(stderr, "maxstart = %d\n", maxstart);
   fprintf(stderr, "Copying database to device...\n");
   t0 = now_ms();
   sats_searcher *sr[MAX_GPUS];
   for (int g = 0; g < ngpus; g++)
-    if (sats_searcher_create(db, g, g, ngpus, &sr[g]) != SATS_OK) die("ERROR creating searcher");
+    if (sats_searcher_create(db, g % have, g, ngpus, &sr[g]) != SATS_OK) die("ERROR creating searcher");
   fprintf(stderr, "Copied %d entries to %d GPU(s) in %f ms\n", dbsize, ngpus, now_ms() - t0);
 
   sats_params prm;
@@ -235,8 +251,36 @@ int main(int argc, char *argv[])
         top_sc = (int32_t *)malloc(sizeof(int32_t) * (size_t)nq * (size_t)hcap);
         top_n = (int32_t *)malloc(sizeof(int32_t) * (size_t)nq);
         if (!top_idx || !top_sc || !top_n) { fprintf(stderr, "malloc failed\n"); exit(1); }
-        if (topk > 0) { if (sats_search_topk(sr[0], topk, top_idx, top_sc) != SATS_OK) die("ERROR selecting top hits"); }
-        else if (sats_search_hits(sr[0], zmin, hcap, top_n, top_idx, top_sc) != SATS_OK) die("ERROR selecting significant hits");
+        /* every shard selects on its own device; the host merges the shards' short lists in the single-GPU row order
+         * (-k: score descending, ties like the device order: larger structures first, then file order; -z: device order) */
+        hit_t *cand = (hit_t *)malloc(sizeof(hit_t) * (size_t)ngpus * (size_t)hcap);
+        int32_t *g_idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)nq * (size_t)hcap);
+        int32_t *g_sc = (int32_t *)malloc(sizeof(int32_t) * (size_t)nq * (size_t)hcap);
+        int32_t *all_idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)ngpus * (size_t)nq * (size_t)hcap);
+        int32_t *all_sc = (int32_t *)malloc(sizeof(int32_t) * (size_t)ngpus * (size_t)nq * (size_t)hcap);
+        if (!cand || !g_idx || !g_sc || !all_idx || !all_sc) { fprintf(stderr, "malloc failed\n"); exit(1); }
+        for (int g = 0; g < ngpus; g++) {
+          if (topk > 0) { if (sats_search_topk(sr[g], topk, g_idx, g_sc) != SATS_OK) die("ERROR selecting top hits"); }
+          else if (sats_search_hits(sr[g], zmin, hcap, top_n, g_idx, g_sc) != SATS_OK) die("ERROR selecting significant hits");
+          memcpy(all_idx + (size_t)g * nq * hcap, g_idx, sizeof(int32_t) * (size_t)nq * (size_t)hcap);
+          memcpy(all_sc + (size_t)g * nq * hcap, g_sc, sizeof(int32_t) * (size_t)nq * (size_t)hcap);
+        }
+        for (int q = 0; q < nq; q++) {
+          int nc = 0;
+          for (int g = 0; g < ngpus; g++)
+            for (int i = 0; i < hcap; i++) {
+              const int32_t e = all_idx[((size_t)g * nq + q) * hcap + i];
+              if (e < 0) break;
+              cand[nc].index = e; cand[nc].score = all_sc[((size_t)g * nq + q) * hcap + i]; cand[nc].order = sats_db_order(db, e);
+              nc++;
+            }
+          qsort(cand, (size_t)nc, sizeof(hit_t), topk > 0 ? by_score_then_device_order : by_device_order);
+          for (int i = 0; i < hcap; i++) {
+            top_idx[(size_t)q * hcap + i] = i < nc ? cand[i].index : -1;
+            top_sc[(size_t)q * hcap + i] = i < nc ? cand[i].score : 0;
+          }
+        }
+        free(cand); free(g_idx); free(g_sc); free(all_idx); free(all_sc);
       } else {
         for (int g = 0; g < ngpus; g++)
           if (sats_search_collect(sr[g], scores, maps) != SATS_OK) die("ERROR collecting results");

@@ -815,7 +815,7 @@ extern "C" int sats_search_hits(sats_searcher *s, double z_min, int cap, int32_t
   if (!(z_min == z_min)) return sats_fail(SATS_ERR_ARG, "sats_search_hits: z_min is NaN");
   CK(cudaSetDevice(s->device));
   const int D = (int)s->sorted_orig.size(), Q = s->last_q, T = SATS_MAXDIM_EXT + 1;
-  cap = std::min(cap, std::max(1, D));
+  const int kcap = std::min(cap, std::max(1, D));      // rows the device keeps per query; the caller's rows stay `cap` wide
   // z is a non-decreasing step function of the raw score for fixed sizes (norm2 = 2 score / (n1 + n2), truncated to int
   // at the z_gumbel call like the reference does): bisect for the first score that passes.  |score| <= 2 C(111, 2) = 12210.
   const int kLo = -16384, kHi = 16384;
@@ -829,7 +829,7 @@ extern "C" int sats_search_hits(sats_searcher *s, double z_min, int cap, int32_t
       thr[(size_t)q * T + n2] = lo;
     }
   // device / pinned buffer: [Q counts][Q bases][cursor][pad][thresholds Q x T][pairs: int2 x Q x cap]
-  const size_t head = 2 * (size_t)Q + 2, pair_off = (head + thr.size() + 1) & ~(size_t)1, words = pair_off + 2 * (size_t)Q * cap;
+  const size_t head = 2 * (size_t)Q + 2, pair_off = (head + thr.size() + 1) & ~(size_t)1, words = pair_off + 2 * (size_t)Q * kcap;
   if (words > s->hits_cap) {
     cudaFree(s->d_hits); cudaFreeHost(s->h_hits);
     s->d_hits = nullptr; s->h_hits = nullptr; s->hits_cap = 0;
@@ -840,7 +840,7 @@ extern "C" int sats_search_hits(sats_searcher *s, double z_min, int cap, int32_t
   memset(s->h_hits, 0, head * 4);
   memcpy(s->h_hits + head, thr.data(), thr.size() * 4);
   CK(cudaMemcpyAsync(s->d_hits, s->h_hits, (head + thr.size()) * 4, cudaMemcpyHostToDevice, s->stream));
-  sats_hits_kernel<<<Q, SATS_TOPK_THREADS, 0, s->stream>>>(s->d_scores, std::max(1, D), D, s->d_sorted_order, s->d_hits + head, cap,
+  sats_hits_kernel<<<Q, SATS_TOPK_THREADS, 0, s->stream>>>(s->d_scores, std::max(1, D), D, s->d_sorted_order, s->d_hits + head, kcap,
                                                            s->d_hits, s->d_hits + Q, reinterpret_cast<int *>(s->d_hits + 2 * Q),
                                                            reinterpret_cast<int2 *>(s->d_hits + pair_off));
   CK(cudaGetLastError());
@@ -854,7 +854,7 @@ extern "C" int sats_search_hits(sats_searcher *s, double z_min, int cap, int32_t
   const int32_t *h_pairs = s->h_hits + pair_off;
   for (int q = 0; q < Q; q++) {
     count_out[q] = h_n[q];
-    const int got = std::min(h_n[q], cap);
+    const int got = std::min(h_n[q], kcap);
     const int32_t *pr = h_pairs + 2 * (size_t)h_base[q];
     for (int i = 0; i < cap; i++) {
       index_out[(size_t)q * cap + i] = i < got ? s->sorted_orig[pr[2 * i]] : -1;

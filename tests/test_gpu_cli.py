@@ -91,10 +91,9 @@ def test_cli_reads_packed_cache(tmp_path, fixtures):
     assert outs[0] == outs[1]
 
 
-@pytest.mark.skipif(S.device_count() < 2, reason="needs two GPUs")
 def test_cli_multi_gpu_output_is_identical(tmp_path, fixtures):
-    """-g 2 shards the database over two GPUs (cost-weighted partition); Philox chains are keyed by original entry
-    index, so stdout must be byte-identical to the single-GPU run."""
+    """-g 2 shards the database over two GPUs (cost-weighted partition; the two shards share the device when the box has
+    one GPU); Philox chains are keyed by original entry index, so stdout must be byte-identical to the single-GPU run."""
     ents = fixtures["small586"]
     qs = [fixtures["queries_by_name"][n] for n in ("D2PHLB1", "SHEETBC")]
     write_ascii_db(tmp_path / "db.ascii", ents)
@@ -146,3 +145,16 @@ def test_cli_significant_hits_only(tmp_path, fixtures):
     assert 0 < total < 2 * len(ents)
     bad = run([CLI, "-r", 8, "-z", "1", "-k", "3"], tmp_path / "q.input", tmp_path)
     assert bad.returncode == 1 and b"cannot be combined" in bad.stderr
+
+
+def test_cli_hit_modes_are_shard_invariant(tmp_path, fixtures):
+    """-k and -z select on every shard's device and merge on the host: three shards print what one prints."""
+    ents = fixtures["small586"]
+    qs = [fixtures["queries_by_name"][n] for n in ("D2PHLB1", "D1UBIA_")]
+    write_ascii_db(tmp_path / "db.ascii", ents)
+    write_query_input(tmp_path / "q.input", "db.ascii", True, False, qs)
+    for extra in (["-k", 40], ["-z", "0.5"]):
+        one = run([CLI, "-r", 64] + extra, tmp_path / "q.input", tmp_path)
+        three = run([CLI, "-r", 64, "-g", 3] + extra, tmp_path / "q.input", tmp_path)
+        assert one.returncode == 0 and three.returncode == 0, three.stderr.decode()[-1000:]
+        assert one.stdout == three.stdout and len(one.stdout) > 1000, extra

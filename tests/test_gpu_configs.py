@@ -207,3 +207,14 @@ def test_device_significance_cut_matches_printed_z_scores(base, fixtures):
             assert (idx[q, len(got):] == -1).all()
     assert cnt.min() == 6000                                   # the last cut (z >= -1e9) keeps everything
     sr.close()
+    # capacity larger than a (sharded) searcher's entry count: rows keep the caller's width
+    part = S.Searcher(db, 0, 1, 40)
+    part.upload(qs)
+    part.launch(S.default_params(lorder=1, lsoln=0, restarts=64, seed=5))
+    cnt, idx, sc = part.hits(-1e9, 1000)
+    assert (cnt == part.entries).all() and part.entries < 1000
+    for q in range(len(qs)):
+        got = idx[q][idx[q] >= 0]
+        assert len(got) == part.entries and (idx[q, part.entries:] == -1).all()
+        assert sc[q, :len(got)].tolist() == full[q][got].tolist()
+    part.close()
