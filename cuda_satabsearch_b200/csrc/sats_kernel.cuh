@@ -4,24 +4,27 @@
 // and its helpers tscord (:306), tmscord (:396), deltasd (:502), thinit (:588), randtypeind (:677).
 // It is a new design, not a translation:
 //
-//   * One LANE runs one restart chain.  A TEAM of TW (32/64/128) threads shares one database entry and
-//     covers `restarts` chains in rounds of TW; a CTA holds several teams (several entries) that share one
-//     copy of the query.  Teams synchronise with named barriers only.
-//   * The query blob and every team's entry blob are brought into shared memory by TMA 1-D bulk copies
-//     (cp.async.bulk ... mbarrier::complete_tx) issued by one thread; everybody waits on the mbarrier.
-//   * Chain state is bit masks in registers (mapped query SSEs, occupied entry SSEs) plus a map of one 32-bit word
-//     per query SSE (the partner's index pre-multiplied by the 8-byte cell size) in lane-private, bank-conflict-free
-//     shared memory.  The LORDER window and the candidate list of the
-//     reference (linear scans, kernel.cu:1053-1083, :677-714) become O(1) mask arithmetic: clz/ffs for the
-//     neighbouring mapped SSEs, (type mask & ~occupied & range mask) for the candidates, popc/select-nth
-//     for the random pick.  deltasd walks only the *mapped* SSEs (set bits), reading one 8-byte
-//     {distance, code} cell per term.
+//   * One LANE runs one restart chain.  A TEAM of TW (32/64/128) threads shares one database entry and covers
+//     `restarts` chains in rounds of TW; a CTA holds several teams that share one copy of the query.  Teams are
+//     persistent: each claims entries of the launch's size-sorted list from a global counter and synchronises with one
+//     named barrier per entry (the arg-max), behind which its leader starts the next entry's copy.
+//   * The query blob and every entry blob are brought into shared memory by TMA 1-D bulk copies (cp.async.bulk ...
+//     mbarrier::complete_tx) issued by one thread, each team on its own mbarrier.
+//   * Chain state is bit masks in registers (mapped query SSEs, occupied entry SSEs) plus a map of one 32-bit word per
+//     query SSE (the partner's index pre-multiplied by the 8-byte cell size) in lane-private, bank-conflict-free shared
+//     memory.  The LORDER window and the candidate list of the reference (linear scans, kernel.cu:1053-1083, :677-714)
+//     become O(1) mask arithmetic: bfind/ffs for the neighbouring mapped SSEs, (type mask & ~occupied & range mask) for
+//     the candidates, popc/select-nth for the random pick.  deltasd walks only the *mapped* SSEs (set bits), reading one
+//     8-byte {distance, code} cell per operand; zeta is a 128-byte shared-memory table indexed by the XOR of two codes;
+//     a missing side of a move reads a row of NaN distances, so the loop body is branch-free.
+//   * LSOLN: the best map is kept as (dirty mask, first-change saves) and completed once per chain, never copied
+//     wholesale.
 //   * Metropolis thresholds come from a host-built table of the reference's exact fp32 values
 //     expf((float)delta / T_m) (kernel.cu:1166) or, in DEVICE_FAST mode, from the same fast-math
 //     intrinsics the reference's GPU build uses.
 //   * Uniforms: Philox4x32-10 at static positions (production) or the reference's XORWOW grid streams
 //     consumed in the reference's order (validation).
-//   * Restart arg-max: redux.sync / ballot inside each warp, then across the team's warps through shared
+//   * Restart arg-max: redux.sync inside each warp, then across the team's warps through shared
 //     memory, with the reference's tie-break (kernel.cu:1205-1221).
 #ifndef SATS_KERNEL_CUH
 #define SATS_KERNEL_CUH
@@ -265,7 +268,7 @@ struct TeamView {
   uint32_t smap;           // this lane's live map (Map<W1 <= 2>)
   uint32_t bmap;           // this lane's best map (Map<false>)
   uint32_t mstride;        // tw * 4: consecutive lanes own consecutive banks, so lane-private accesses never conflict
-  int n1, n2, tw;
+  int n1, n2;
 };
 
 // Lane-private maps (query SSE -> partner entry SSE) in two representations, both laid out so that consecutive lanes own
@@ -620,7 +623,6 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
   __syncthreads();
 
   TeamView v;
-  v.tw = p.tw;
   v.mstride = (uint32_t)p.tw * 4u;
   v.qtype = sq + 16;
   // Queries of more than 64 SSEs (W1 == 4) keep their n1 x n1 cells in global memory (read through L1 with ld.global.nc):
