@@ -85,8 +85,12 @@ struct sats_searcher {
   uint8_t *d_qblobs = nullptr; size_t qblob_cap = 0;
   uint64_t *d_qoff = nullptr; uint32_t *d_qbytes = nullptr; int qmeta_cap = 0;
   uint8_t *h_qstage = nullptr; size_t h_qstage_cap = 0;
-  std::vector<int> q_n1;
-  std::vector<uint32_t> q_bytes;
+  // Queries live on the device in SLOTS: the batch sorted (stably) by size class, so that a launch -- which sizes its
+  // shared memory for the largest query it covers -- spans queries of similar size.  slot_q[slot] = position in the batch.
+  std::vector<int> q_n1;               // by slot
+  std::vector<uint32_t> q_bytes;       // by slot
+  std::vector<int> slot_q;
+  int32_t *d_qorig = nullptr;          // by slot: position in the batch (keys the Philox streams)
   // results
   int32_t *d_scores = nullptr; int8_t *d_maps = nullptr;
   int32_t *h_scores = nullptr; int8_t *h_maps = nullptr;
@@ -109,6 +113,14 @@ static kernel_fn pick_kernel(int w1, int w2, bool lorder, bool xorwow, bool lsol
   }
 }
 static int words_for(int n) { return n <= 32 ? 1 : (n <= 64 ? 2 : 4); }
+// query size classes (upper bounds of the order): one launch never mixes classes
+static int query_class(int n)
+{
+  static const int bounds[] = {8, 12, 16, 20, 24, 32, 48, 64};
+  int c = 0;
+  while (c < 8 && n > bounds[c]) c++;
+  return c;
+}
 static size_t round16(size_t x) { return (x + 15) & ~(size_t)15; }
 static size_t entry_blob_bytes(int n) { return round16(SATS_K_ENTRY_HDR + 8 * (size_t)n * n); }
 static size_t query_blob_bytes(int n) { return round16(SATS_K_QUERY_HDR + 8 * (size_t)n * n); }
@@ -227,7 +239,7 @@ extern "C" void sats_searcher_free(sats_searcher *s)
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
   cudaFree(s->d_blobs); cudaFree(s->d_blob_off); cudaFree(s->d_blob_bytes); cudaFree(s->d_accept); cudaFree(s->d_xw);
-  cudaFree(s->d_pool_list); cudaFree(s->d_xw_blocks); cudaFree(s->d_counters); cudaFree(s->d_qblobs); cudaFree(s->d_qoff); cudaFree(s->d_qbytes);
+  cudaFree(s->d_pool_list); cudaFree(s->d_xw_blocks); cudaFree(s->d_counters); cudaFree(s->d_qblobs); cudaFree(s->d_qoff); cudaFree(s->d_qbytes); cudaFree(s->d_qorig);
   cudaFree(s->d_scores); cudaFree(s->d_maps); cudaFree(s->d_topk); cudaFreeHost(s->h_topk);
   cudaFree(s->d_sorted_order); cudaFree(s->d_hits); cudaFreeHost(s->h_hits);
   if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
@@ -285,17 +297,25 @@ extern "C" int sats_search_upload(sats_searcher *s, const sats_db *queries, int 
   CK(cudaStreamSynchronize(s->stream));   // staging buffers may still be in flight
   size_t total = 0;
   std::vector<uint64_t> off((size_t)qcount);
-  s->q_n1.assign((size_t)qcount, 0);
-  s->q_bytes.assign((size_t)qcount, 0);
   for (int q = 0; q < qcount; q++) {
     int n = queries->order[qfirst + q];
     if (n > SATS_MAXDIM) return sats_fail(SATS_ERR_ARG, "query %s has order %d; queries are limited to %d SSEs", queries->name(qfirst + q), n, SATS_MAXDIM);
-    s->q_n1[q] = n;
-    off[q] = total;
-    s->q_bytes[q] = (uint32_t)query_blob_bytes(n);
-    total += s->q_bytes[q];
   }
-  size_t meta = (size_t)qcount * 12;
+  s->slot_q.resize((size_t)qcount);
+  std::iota(s->slot_q.begin(), s->slot_q.end(), 0);
+  std::stable_sort(s->slot_q.begin(), s->slot_q.end(), [&](int a, int b) {
+    return query_class(queries->order[qfirst + a]) < query_class(queries->order[qfirst + b]);
+  });
+  s->q_n1.assign((size_t)qcount, 0);
+  s->q_bytes.assign((size_t)qcount, 0);
+  for (int slot = 0; slot < qcount; slot++) {
+    int n = queries->order[qfirst + s->slot_q[slot]];
+    s->q_n1[slot] = n;
+    off[slot] = total;
+    s->q_bytes[slot] = (uint32_t)query_blob_bytes(n);
+    total += s->q_bytes[slot];
+  }
+  size_t meta = (size_t)qcount * 16;
   if (total + meta > s->h_qstage_cap) {
     cudaFreeHost(s->h_qstage);
     s->h_qstage = nullptr;
@@ -311,16 +331,17 @@ extern "C" int sats_search_upload(sats_searcher *s, const sats_db *queries, int 
     s->qblob_cap = total;
   }
   if (qcount > s->qmeta_cap) {
-    cudaFree(s->d_qoff); cudaFree(s->d_qbytes);
-    s->d_qoff = nullptr; s->d_qbytes = nullptr; s->qmeta_cap = 0;
+    cudaFree(s->d_qoff); cudaFree(s->d_qbytes); cudaFree(s->d_qorig);
+    s->d_qoff = nullptr; s->d_qbytes = nullptr; s->d_qorig = nullptr; s->qmeta_cap = 0;
     CK(cudaMalloc(&s->d_qoff, (size_t)qcount * 8));
     CK(cudaMalloc(&s->d_qbytes, (size_t)qcount * 4));
+    CK(cudaMalloc(&s->d_qorig, (size_t)qcount * 4));
     s->qmeta_cap = qcount;
   }
   memset(s->h_qstage, 0, total);
-  for (int q = 0; q < qcount; q++) {
-    int e = qfirst + q, n = queries->order[e];
-    uint8_t *b = s->h_qstage + off[q];
+  for (int slot = 0; slot < qcount; slot++) {
+    int e = qfirst + s->slot_q[slot], n = queries->order[e];
+    uint8_t *b = s->h_qstage + off[slot];
     int32_t hdr[4] = {n, 0, 0, 0};     // hdr[1] (Philox query index) is patched at launch via q_index_base
     memcpy(b, hdr, 16);
     for (int i = 0; i < n; i++) b[16 + i] = queries->code(e, i, i);
@@ -328,18 +349,20 @@ extern "C" int sats_search_upload(sats_searcher *s, const sats_db *queries, int 
   }
   memcpy(s->h_qstage + total, off.data(), (size_t)qcount * 8);
   memcpy(s->h_qstage + total + (size_t)qcount * 8, s->q_bytes.data(), (size_t)qcount * 4);
+  memcpy(s->h_qstage + total + (size_t)qcount * 12, s->slot_q.data(), (size_t)qcount * 4);
   CK(cudaMemcpyAsync(s->d_qblobs, s->h_qstage, total, cudaMemcpyHostToDevice, s->stream));
   CK(cudaMemcpyAsync(s->d_qoff, s->h_qstage + total, (size_t)qcount * 8, cudaMemcpyHostToDevice, s->stream));
   CK(cudaMemcpyAsync(s->d_qbytes, s->h_qstage + total + (size_t)qcount * 8, (size_t)qcount * 4, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaMemcpyAsync(s->d_qorig, s->h_qstage + total + (size_t)qcount * 12, (size_t)qcount * 4, cudaMemcpyHostToDevice, s->stream));
   s->last_q = qcount;
   return SATS_OK;
 }
 
 // writes the Philox query index into the device copies of the query headers
-__global__ void sats_patch_query_index(uint8_t *qblobs, const uint64_t *qoff, int qcount, uint32_t base)
+__global__ void sats_patch_query_index(uint8_t *qblobs, const uint64_t *qoff, const int32_t *qorig, int qcount, uint32_t base)
 {
-  int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q < qcount) reinterpret_cast<uint32_t *>(qblobs + qoff[q])[1] = base + (uint32_t)q;
+  int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot < qcount) reinterpret_cast<uint32_t *>(qblobs + qoff[slot])[1] = base + (uint32_t)qorig[slot];
 }
 
 static int ensure_results(sats_searcher *s, int qcount, int lsoln)
@@ -397,7 +420,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
   s->last_lsoln = pp->lsoln;
   CK(cudaMemsetAsync(s->d_scores, 0x80, (size_t)Q * std::max(1, D) * 4, s->stream));
   if (elapsed_ms) CK(cudaEventRecord(s->ev0, s->stream));
-  sats_patch_query_index<<<(Q + 127) / 128, 128, 0, s->stream>>>(s->d_qblobs, s->d_qoff, Q, query_index_base);
+  sats_patch_query_index<<<(Q + 127) / 128, 128, 0, s->stream>>>(s->d_qblobs, s->d_qoff, s->d_qorig, Q, query_index_base);
   CK(cudaGetLastError());
   s->launches++;
 
@@ -439,7 +462,10 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
       k.tw = SATS_REF_GRID_THREADS; k.teams = 1;
       k.sm_entry_bytes = (int)entry_blob_bytes(n2max);
       k.sm_nan_bytes = (int)round16(8 * (size_t)n2max);
-      for (int q = 0; q < Q; q++) {    // one launch per query, in order: the streams carry over
+      std::vector<int> slot_of((size_t)Q);
+      for (int slot = 0; slot < Q; slot++) slot_of[s->slot_q[slot]] = slot;
+      for (int qo = 0; qo < Q; qo++) {    // one launch per query, in the batch's order: the streams carry over
+        const int q = slot_of[qo];
         const int n1 = s->q_n1[q];
         k.q_first = q;
         k.sm_query_bytes = words_for(n1) > 2 ? SATS_K_QUERY_HDR : (int)s->q_bytes[q];
@@ -469,7 +495,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
       for (int q0 = 0; q0 < Q;) {
         int q1 = q0 + 1;
         const int w1 = words_for(s->q_n1[q0]);
-        while (q1 < Q && words_for(s->q_n1[q1]) == w1 && q1 - q0 < 65535) q1++;   // gridDim.y limit
+        while (q1 < Q && query_class(s->q_n1[q1]) == query_class(s->q_n1[q0]) && q1 - q0 < 65535) q1++;   // gridDim.y limit
         int n1max = 0; uint32_t qbmax = 0;
         for (int q = q0; q < q1; q++) { n1max = std::max(n1max, s->q_n1[q]); qbmax = std::max(qbmax, s->q_bytes[q]); }
         k.q_first = q0;
@@ -602,7 +628,7 @@ extern "C" int sats_search_collect(sats_searcher *s, int32_t *scores, int32_t *m
     for (int kpos = 0; kpos < D; kpos++) {
       int v = s->h_scores[(size_t)q * D + kpos];
       if (v == kScoreSentinel) continue;
-      size_t o = (size_t)q * s->db_count + s->sorted_orig[kpos];
+      size_t o = (size_t)s->slot_q[q] * s->db_count + s->sorted_orig[kpos];
       scores[o] = v;
       if (s->last_lsoln) {
         const int8_t *row = s->h_maps + ((size_t)q * D + kpos) * SATS_K_MAPROW;
@@ -748,8 +774,8 @@ extern "C" int sats_search_topk(sats_searcher *s, int k, int32_t *index_out, int
         return a < b;
       });
       for (int i = 0; i < k; i++) {
-        index_out[(size_t)q * k + i] = i < got ? s->sorted_orig[rowpos[i]] : -1;
-        score_out[(size_t)q * k + i] = i < got ? rowbuf[rowpos[i]] : INT_MIN;
+        index_out[(size_t)s->slot_q[q] * k + i] = i < got ? s->sorted_orig[rowpos[i]] : -1;
+        score_out[(size_t)s->slot_q[q] * k + i] = i < got ? rowbuf[rowpos[i]] : INT_MIN;
       }
       continue;
     }
@@ -761,11 +787,11 @@ extern "C" int sats_search_topk(sats_searcher *s, int k, int32_t *index_out, int
     });
     for (int i = 0; i < k; i++) {
       if (i < got) {
-        index_out[(size_t)q * k + i] = s->sorted_orig[h_pos[(size_t)q * k + order[i]]];
-        score_out[(size_t)q * k + i] = h_sc[(size_t)q * k + order[i]];
+        index_out[(size_t)s->slot_q[q] * k + i] = s->sorted_orig[h_pos[(size_t)q * k + order[i]]];
+        score_out[(size_t)s->slot_q[q] * k + i] = h_sc[(size_t)q * k + order[i]];
       } else {
-        index_out[(size_t)q * k + i] = -1;
-        score_out[(size_t)q * k + i] = INT_MIN;
+        index_out[(size_t)s->slot_q[q] * k + i] = -1;
+        score_out[(size_t)s->slot_q[q] * k + i] = INT_MIN;
       }
     }
   }
@@ -853,12 +879,13 @@ extern "C" int sats_search_hits(sats_searcher *s, double z_min, int cap, int32_t
   CK(cudaStreamSynchronize(s->stream));
   const int32_t *h_pairs = s->h_hits + pair_off;
   for (int q = 0; q < Q; q++) {
-    count_out[q] = h_n[q];
+    const size_t row = (size_t)s->slot_q[q];          // output rows follow the batch, device rows the slots
+    count_out[row] = h_n[q];
     const int got = std::min(h_n[q], kcap);
     const int32_t *pr = h_pairs + 2 * (size_t)h_base[q];
     for (int i = 0; i < cap; i++) {
-      index_out[(size_t)q * cap + i] = i < got ? s->sorted_orig[pr[2 * i]] : -1;
-      score_out[(size_t)q * cap + i] = i < got ? pr[2 * i + 1] : INT_MIN;
+      index_out[row * cap + i] = i < got ? s->sorted_orig[pr[2 * i]] : -1;
+      score_out[row * cap + i] = i < got ? pr[2 * i + 1] : INT_MIN;
     }
   }
   return SATS_OK;
