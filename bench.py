@@ -290,7 +290,7 @@ def ours(args):
     if pj.exists():
         prof = json.loads(pj.read_text())
     orders = db.orders().astype(np.int64)
-    blob_bytes = float(((80 + 8 * orders * orders + 15) // 16 * 16).sum())      # every entry blob is read once per query
+    blob_bytes = float(((80 + 8 * orders * (orders + 1) + 15) // 16 * 16).sum())      # every entry blob is read once per query
     roofline = {
         "bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
         "traffic": prof.get("dram_bytes_per_step"),

@@ -122,7 +122,7 @@ static int query_class(int n)
   return c;
 }
 static size_t round16(size_t x) { return (x + 15) & ~(size_t)15; }
-static size_t entry_blob_bytes(int n) { return round16(SATS_K_ENTRY_HDR + 8 * (size_t)n * n); }
+static size_t entry_blob_bytes(int n) { return round16(SATS_K_ENTRY_HDR + 8 * (size_t)n * (n + 1)); }     // header, NaN row, n x n cells
 static size_t query_blob_bytes(int n) { return round16(SATS_K_QUERY_HDR + 8 * (size_t)n * n); }
 
 static void fill_cells(const sats_db *db, int e, uint8_t *cells)
@@ -192,7 +192,10 @@ extern "C" int sats_searcher_create(const sats_db *db, int device, int shard_ran
     uint32_t tm[4][4] = {{0}};
     for (int j = 0; j < n; j++) tm[db->code(e, j, j) & 3][j >> 5] |= 1u << (j & 31);
     memcpy(b + 16, tm, 64);
-    fill_cells(db, e, b + SATS_K_ENTRY_HDR);
+    // "row -1": n cells of NaN distance right in front of the matrix, so that the missing side of a move (partner -1)
+    // addresses a row whose gate never opens without any special casing in the kernel
+    for (int j = 0; j < n; j++) { const uint32_t nan_cell[2] = {0x7fc00000u, 0u}; memcpy(b + SATS_K_ENTRY_HDR + 8 * (size_t)j, nan_cell, 8); }
+    fill_cells(db, e, b + SATS_K_ENTRY_HDR + 8 * (size_t)n);
   }
   auto fail = [&](int rc) { sats_searcher_free(s); return rc; };
 #define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(sats_fail(SATS_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_))); } while (0)
@@ -461,7 +464,6 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
       k.pool_count = (int)list.size();
       k.tw = SATS_REF_GRID_THREADS; k.teams = 1;
       k.sm_entry_bytes = (int)entry_blob_bytes(n2max);
-      k.sm_nan_bytes = (int)round16(8 * (size_t)n2max);
       std::vector<int> slot_of((size_t)Q);
       for (int slot = 0; slot < Q; slot++) slot_of[s->slot_q[slot]] = slot;
       for (int qo = 0; qo < Q; qo++) {    // one launch per query, in the batch's order: the streams carry over
@@ -473,7 +475,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
         k.sm_bmapwords = pp->lsoln ? (n1 + 3) / 4 : 0;
         k.sm_qmask_bytes = (int)round16((size_t)n1 * words_for(n2max) * 4);
         k.sm_team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * k.tw * 4 + SATS_K_SCRATCH_BYTES + (size_t)(k.tw / 32) * k.sm_qmask_bytes);
-        size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + k.sm_nan_bytes + SATS_K_ZTAB_BYTES + k.sm_team_bytes;
+        size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + SATS_K_ZTAB_BYTES + k.sm_team_bytes;
         if (smem > (size_t)kMaxSmem) return sats_fail(SATS_ERR_ARG, "query %d x entry order %d needs %zu B of shared memory", q, n2max, smem);
         kernel_fn fn = pick_kernel(words_for(n1), words_for(n2max), pp->lorder != 0, true, pp->lsoln != 0);
         fn<<<dim3((unsigned)blocks.size(), 1), k.tw, smem, s->stream>>>(k);
@@ -511,8 +513,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
           int b1 = b0;
           while (b1 < r1 && s->sorted_order[b1] > lowbound) b1++;
           k.sm_entry_bytes = (int)entry_blob_bytes(n2max);
-          k.sm_nan_bytes = (int)round16(8 * (size_t)n2max);
-          k.sm_qmask_bytes = (int)round16((size_t)n1max * words_for(n2max) * 4);
+              k.sm_qmask_bytes = (int)round16((size_t)n1max * words_for(n2max) * 4);
           kernel_fn fn = pick_kernel(w1, words_for(n2max), pp->lorder != 0, false, pp->lsoln != 0);
           // team width (threads sharing one entry; results do not depend on it) and teams per CTA: whatever keeps the
           // most warps resident per SM; a narrower team only when it buys strictly more
@@ -531,7 +532,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
               int teams_max = SATS_K_MAXTHREADS / tw;
               if (const char *e = getenv("SATS_TEAMS")) teams_max = std::max(1, std::min(teams_max, atoi(e)));
               for (int teams = teams_max; teams >= 1; teams--) {
-                size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + k.sm_nan_bytes + SATS_K_ZTAB_BYTES + (size_t)teams * team_bytes;
+                size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + SATS_K_ZTAB_BYTES + (size_t)teams * team_bytes;
                 if (smem > (size_t)kMaxSmem) continue;
                 int ctas = 0;
                 CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, fn, teams * tw, smem));
@@ -547,7 +548,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
           k.teams = best_teams;
           k.sm_team_bytes = best_team_bytes;
           k.item_first = b0; k.item_count = b1 - b0;
-          size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + k.sm_nan_bytes + SATS_K_ZTAB_BYTES + (size_t)k.teams * k.sm_team_bytes;
+          size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + SATS_K_ZTAB_BYTES + (size_t)k.teams * k.sm_team_bytes;
           // persistent teams: no more CTAs than fit on the device at once (per query); each team keeps claiming entries
           k.counters = s->d_counters + counter_base;
           counter_base += (size_t)(q1 - q0);

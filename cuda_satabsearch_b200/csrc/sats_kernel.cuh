@@ -260,8 +260,7 @@ struct TeamView {
   const uint2 *qcell_g;    // W1 == 4 only: the query's n1 x n1 cells in global memory
   uint32_t qcell;          // n1 x n1 {distance bits, code} (W1 <= 2)
   const uint8_t *qtype;    // n1
-  uint32_t ecell;          // n2 x n2
-  uint32_t nanrow;         // one row of cells whose distance is NaN: stands in for the missing side of a move
+  uint32_t ecell;          // n2 x n2, preceded by "row -1": n2 cells of NaN distance (the missing side of a move)
   uint32_t ztab;           // the zeta table (128-byte aligned)
   const uint32_t *tmask;   // [4][4] type -> 128-bit mask of entry SSEs of that type
   uint32_t qmask;          // [n1][W2] per query SSE: the mask of entry SSEs of its type (built per entry, one load per move)
@@ -404,8 +403,8 @@ struct Chain {
     int d = 0;
     const uint2 *qrow_g = v.qcell_g + i * v.n1;                         // W1 == 4: query cells live in global memory
     uint32_t qrow = W1 > 2 ? 0u : v.qcell + (uint32_t)(i * v.n1) * 8u;  // row base addresses, hoisted by hand
-    uint32_t frow = from >= 0 ? v.ecell + (uint32_t)(from * v.n2) * 8u : v.nanrow;
-    uint32_t trow = to >= 0 ? v.ecell + (uint32_t)(to * v.n2) * 8u : v.nanrow;
+    uint32_t frow = v.ecell + (uint32_t)(from * v.n2) * 8u;         // from / to = -1: the NaN row in front of the matrix
+    uint32_t trow = v.ecell + (uint32_t)(to * v.n2) * 8u;
     asm volatile("" : "+r"(qrow), "+r"(frow), "+r"(trow));       // keep the compiler from re-folding them into the loop
 #pragma unroll
     for (int w = 0; w < W1; w++) {
@@ -479,8 +478,13 @@ struct Chain {
     }
     if (accept) {
       score = cand_score;
-      if (from >= 0) bit_clear<W2>(md, from);
-      if (to >= 0) { bit_set<W2>(md, to); bit_set<W1>(mq, i); }
+      if (W2 == 1) {
+        md[0] = (md[0] & ~bit_in_word(from, 0)) | bit_in_word(to, 0);       // shl.b32 clamps: "bit -1" is no bit, no selects
+      } else {
+        if (from >= 0) bit_clear<W2>(md, from);
+        if (to >= 0) bit_set<W2>(md, to);
+      }
+      if (to >= 0) bit_set<W1>(mq, i);
       else bit_clear<W1>(mq, i);
       if (from >= 0 || to >= 0) {
         if (LSOLN && !improved && owned && !bit_test<W1>(dirty, i)) {
@@ -596,7 +600,6 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
 //   [0, 128)                    mbarriers: one for the query, one per team
 //   then 256 B                  the 128-byte zeta table at the first 128-byte aligned address
 //   then sm_query_bytes         query blob (header + SSE types only when W1 == 4)
-//   then sm_nan_bytes           one row of {NaN, 0} cells
 //   then per team: entry blob (sm_entry_bytes) | live maps (mapwords*tw*4) | best maps (bmapwords*tw*4) | 80 B scratch (2 arg-max buffers, 2 claim slots) | one qmask (n1 x W2 words) per warp
 template <int W1, int W2, bool LORDER, bool XORWOW, bool LSOLN>
 __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anneal_kernel(const SatsKParams p)
@@ -607,9 +610,8 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
   const uint32_t zpad = (0u - (smem_u32(smem) + SATS_K_BAR_BYTES)) & 127u;       // up to the next 128-byte aligned address
   int8_t *sz = reinterpret_cast<int8_t *>(smem + SATS_K_BAR_BYTES + zpad);
   uint8_t *sq = smem + SATS_K_BAR_BYTES + SATS_K_ZTAB_BYTES;
-  uint2 *snan = reinterpret_cast<uint2 *>(sq + p.sm_query_bytes);
   const int team = threadIdx.x / p.tw, tl = threadIdx.x - team * p.tw;
-  uint8_t *steam = smem + SATS_K_BAR_BYTES + SATS_K_ZTAB_BYTES + p.sm_query_bytes + p.sm_nan_bytes + (size_t)team * p.sm_team_bytes;
+  uint8_t *steam = smem + SATS_K_BAR_BYTES + SATS_K_ZTAB_BYTES + p.sm_query_bytes + (size_t)team * p.sm_team_bytes;
   uint8_t *se = steam;
   uint8_t *smaps = se + p.sm_entry_bytes;
   uint8_t *bmaps = smaps + p.sm_mapwords * p.tw * 4;
@@ -618,7 +620,6 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
   const int qi = p.q_first + blockIdx.y;     // query slot of this batch: selects the blob and the output row
   if (threadIdx.x == 0)
     for (int t = 0; t <= p.teams; t++) mbar_init(bar + t, 1);
-  for (int c = threadIdx.x; c < (p.sm_nan_bytes >> 3); c += blockDim.x) snan[c] = make_uint2(0x7fc00000u, 0u);
   fill_zeta_table(sz, threadIdx.x, blockDim.x);
   __syncthreads();
 
@@ -629,10 +630,9 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
   // an 82 KB query copy per CTA would leave room for one CTA per SM.  Only header + SSE types are staged then.
   v.qcell_g = reinterpret_cast<const uint2 *>(p.qblobs + p.qblob_off[qi] + SATS_K_QUERY_HDR);
   v.qcell = smem_u32(sq + SATS_K_QUERY_HDR);
-  v.nanrow = smem_u32(snan);
   v.ztab = smem_u32(sz);
   v.tmask = reinterpret_cast<const uint32_t *>(se + 16);
-  v.ecell = smem_u32(se + SATS_K_ENTRY_HDR);
+  const uint32_t ecell0 = smem_u32(se + SATS_K_ENTRY_HDR);      // the matrix starts one row (8 n2 bytes) further: set per entry
   v.smap = smem_u32(smaps + tl * 4);
   v.bmap = smem_u32(bmaps + tl * 4);
   // team scratch: red[2][4] (two alternating arg-max buffers) | claim[2] | per-warp qmask copies
@@ -683,6 +683,7 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
       mbar_wait(tbar, phase);
       phase ^= 1u;
       v.n2 = eh[0];
+      v.ecell = ecell0 + 8u * (uint32_t)v.n2;
       anneal_entry<W1, W2, LORDER, false, LSOLN>(p, v, team, tl, red + 4 * par, (uint32_t)eh[1], (uint32_t)qh[1], xw, qi, p.item_first + idx,
                                                  [&] { if (tl == 0) claim_next(par ^ 1); },
                                                  [&] { if (tl == 0) fetch(claim[par ^ 1]); });
@@ -713,6 +714,7 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
       phase ^= 1u;
       const int32_t *eh = reinterpret_cast<const int32_t *>(se);
       v.n2 = eh[0];
+      v.ecell = ecell0 + 8u * (uint32_t)v.n2;
       anneal_entry<W1, W2, LORDER, true, LSOLN>(p, v, 0, tl, red, (uint32_t)eh[1], (uint32_t)qh[1], xw, qi, e, [] {}, [] {});
       __syncthreads();       // the entry buffer and the arg-max scratch are reused by the next entry
     }

@@ -8,7 +8,7 @@
 #define SATS_K_MOVES 100
 #define SATS_K_DCLAMP 229          // expf(-d/T) <= 2^-33 (smallest uniform) for every d >= 229 and T <= 10
 #define SATS_K_NEG_INIT (-99999)
-#define SATS_K_ENTRY_HDR 80        // 16 B header + 4 types x 4 words of type masks
+#define SATS_K_ENTRY_HDR 80        // 16 B header + 4 types x 4 words of type masks; then one row of NaN cells, then the matrix
 #define SATS_K_QUERY_HDR 128       // 16 B header + 112 B of SSE types
 #define SATS_K_BAR_BYTES 128       // shared-memory header: 1 + teams mbarriers (teams <= 12)
 #define SATS_K_ZTAB_BYTES 256      // shared-memory room for the 128-byte zeta table at a 128-byte aligned address
@@ -39,7 +39,6 @@ struct SatsKParams {
   int teams;                       // teams per CTA
   int sm_query_bytes;              // room for the largest query blob of this launch
   int sm_entry_bytes;              // room for the largest entry blob of this launch
-  int sm_nan_bytes;                // room for one row of NaN-distance cells (8 B x largest entry order of this launch)
   int sm_mapwords;                 // 32-bit words per live chain map: n1max (queries of <= 64 SSEs) or ceil(n1max / 4)
   int sm_bmapwords;                // 32-bit words per best map: ceil(n1max / 4) with lsoln, else 0
   int sm_qmask_bytes;              // per warp: room for n1max x W2 words (16-byte multiple)
