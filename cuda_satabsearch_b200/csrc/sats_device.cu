@@ -471,7 +471,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
         const int n1 = s->q_n1[q];
         k.q_first = q;
         k.sm_query_bytes = words_for(n1) > 2 ? SATS_K_QUERY_HDR : (int)s->q_bytes[q];
-        k.sm_mapwords = words_for(n1) > 2 ? (n1 + 3) / 4 : n1;
+        k.sm_mapwords = words_for(n1) > 2 ? (n1 + 3) / 4 : n1 + 1;      // word maps carry an element -1
         k.sm_bmapwords = pp->lsoln ? (n1 + 3) / 4 : 0;
         k.sm_qmask_bytes = (int)round16((size_t)n1 * words_for(n2max) * 4);
         k.sm_team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * k.tw * 4 + SATS_K_SCRATCH_BYTES + (size_t)(k.tw / 32) * k.sm_qmask_bytes);
@@ -502,7 +502,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
         for (int q = q0; q < q1; q++) { n1max = std::max(n1max, s->q_n1[q]); qbmax = std::max(qbmax, s->q_bytes[q]); }
         k.q_first = q0;
         k.sm_query_bytes = w1 > 2 ? SATS_K_QUERY_HDR : (int)qbmax;
-        k.sm_mapwords = w1 > 2 ? (n1max + 3) / 4 : n1max;
+        k.sm_mapwords = w1 > 2 ? (n1max + 3) / 4 : n1max + 1;      // word maps carry an element -1
         k.sm_bmapwords = pp->lsoln ? (n1max + 3) / 4 : 0;
         int b0 = r0;
         while (b0 < r1) {

@@ -434,7 +434,8 @@ struct Chain {
     int lo, hi, from;
     if (LORDER) {
       int kp = top_at_or_below<W1>(mq, i);
-      lo = kp >= 0 ? LiveMap::get(v.smap, kp, v.mstride) : v.n2;
+      // word maps keep n2 in "element -1" (written once per entry), so a missing lower neighbour needs no select
+      lo = (W1 <= 2) ? LiveMap::get(v.smap, kp, v.mstride) : (kp >= 0 ? LiveMap::get(v.smap, kp, v.mstride) : v.n2);
       from = was_mapped ? lo : -1;
       const int kn = low_at_or_above<W1>(mq, i + 1);            // -1 for the last query SSE: nothing above it
       hi = kn >= 0 ? LiveMap::get(v.smap, kn, v.mstride) : -1;
@@ -512,6 +513,7 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
 #pragma unroll
     for (int w = 0; w < W2; w++) asm volatile("st.shared.b32 [%0], %1;" ::"r"(v.qmask + (uint32_t)(k * W2 + w) * 4u), "r"(tm[w]) : "memory");
   }
+  if (W1 <= 2) Map<true>::put(v.smap, -1, v.mstride, v.n2);       // see Chain::move: the lower window bound of "nothing mapped below"
   __syncwarp();
   Chain<W1, W2, LORDER, XORWOW, LSOLN> ch;
   int best = SATS_K_NEG_INIT;
@@ -633,7 +635,7 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
   v.ztab = smem_u32(sz);
   v.tmask = reinterpret_cast<const uint32_t *>(se + 16);
   const uint32_t ecell0 = smem_u32(se + SATS_K_ENTRY_HDR);      // the matrix starts one row (8 n2 bytes) further: set per entry
-  v.smap = smem_u32(smaps + tl * 4);
+  v.smap = smem_u32(smaps + tl * 4) + (W1 <= 2 ? (uint32_t)p.tw * 4u : 0u);      // word maps: element -1 exists
   v.bmap = smem_u32(bmaps + tl * 4);
   // team scratch: red[2][4] (two alternating arg-max buffers) | claim[2] | per-warp qmask copies
   volatile int *claim = reinterpret_cast<volatile int *>(red + 8);
