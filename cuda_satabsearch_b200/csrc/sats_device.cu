@@ -113,10 +113,12 @@ static kernel_fn pick_kernel(int w1, int w2, bool lorder, bool xorwow, bool lsol
   }
 }
 static int words_for(int n) { return n <= 32 ? 1 : (n <= 64 ? 2 : 4); }
+// mask words of a QUERY: one bit more than its order, for the sentinel "SSE n1" the kernel keeps above the last one
+static int qwords_for(int n) { return n < 32 ? 1 : (n < 64 ? 2 : 4); }
 // query size classes (upper bounds of the order): one launch never mixes classes
 static int query_class(int n)
 {
-  static const int bounds[] = {8, 12, 16, 20, 24, 32, 48, 64};
+  static const int bounds[] = {8, 12, 16, 20, 24, 31, 48, 63};      // 31 / 63: the last orders whose masks fit 1 / 2 words
   int c = 0;
   while (c < 8 && n > bounds[c]) c++;
   return c;
@@ -470,14 +472,14 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
         const int q = slot_of[qo];
         const int n1 = s->q_n1[q];
         k.q_first = q;
-        k.sm_query_bytes = words_for(n1) > 2 ? SATS_K_QUERY_HDR : (int)s->q_bytes[q];
-        k.sm_mapwords = words_for(n1) > 2 ? (n1 + 3) / 4 : n1 + 1;      // word maps carry an element -1
+        k.sm_query_bytes = qwords_for(n1) > 2 ? SATS_K_QUERY_HDR : (int)s->q_bytes[q];
+        k.sm_mapwords = qwords_for(n1) > 2 ? (n1 + 3) / 4 : n1 + 2;      // word maps carry elements -1 and n1
         k.sm_bmapwords = pp->lsoln ? (n1 + 3) / 4 : 0;
         k.sm_qmask_bytes = (int)round16((size_t)n1 * words_for(n2max) * 4);
         k.sm_team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * k.tw * 4 + SATS_K_SCRATCH_BYTES + (size_t)(k.tw / 32) * k.sm_qmask_bytes);
         size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + SATS_K_ZTAB_BYTES + k.sm_team_bytes;
         if (smem > (size_t)kMaxSmem) return sats_fail(SATS_ERR_ARG, "query %d x entry order %d needs %zu B of shared memory", q, n2max, smem);
-        kernel_fn fn = pick_kernel(words_for(n1), words_for(n2max), pp->lorder != 0, true, pp->lsoln != 0);
+        kernel_fn fn = pick_kernel(qwords_for(n1), words_for(n2max), pp->lorder != 0, true, pp->lsoln != 0);
         fn<<<dim3((unsigned)blocks.size(), 1), k.tw, smem, s->stream>>>(k);
         CK(cudaGetLastError());
         s->launches++;
@@ -496,13 +498,13 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
       // runs of consecutive queries with the same mask width share launches (grid.y)
       for (int q0 = 0; q0 < Q;) {
         int q1 = q0 + 1;
-        const int w1 = words_for(s->q_n1[q0]);
+        const int w1 = qwords_for(s->q_n1[q0]);
         while (q1 < Q && query_class(s->q_n1[q1]) == query_class(s->q_n1[q0]) && q1 - q0 < 65535) q1++;   // gridDim.y limit
         int n1max = 0; uint32_t qbmax = 0;
         for (int q = q0; q < q1; q++) { n1max = std::max(n1max, s->q_n1[q]); qbmax = std::max(qbmax, s->q_bytes[q]); }
         k.q_first = q0;
         k.sm_query_bytes = w1 > 2 ? SATS_K_QUERY_HDR : (int)qbmax;
-        k.sm_mapwords = w1 > 2 ? (n1max + 3) / 4 : n1max + 1;      // word maps carry an element -1
+        k.sm_mapwords = w1 > 2 ? (n1max + 3) / 4 : n1max + 2;      // word maps carry elements -1 and n1
         k.sm_bmapwords = pp->lsoln ? (n1max + 3) / 4 : 0;
         int b0 = r0;
         while (b0 < r1) {

@@ -437,8 +437,17 @@ struct Chain {
       // word maps keep n2 in "element -1" (written once per entry), so a missing lower neighbour needs no select
       lo = (W1 <= 2) ? LiveMap::get(v.smap, kp, v.mstride) : (kp >= 0 ? LiveMap::get(v.smap, kp, v.mstride) : v.n2);
       from = was_mapped ? lo : -1;
-      const int kn = low_at_or_above<W1>(mq, i + 1);            // -1 for the last query SSE: nothing above it
-      hi = kn >= 0 ? LiveMap::get(v.smap, kn, v.mstride) : -1;
+      if (W1 <= 2) {
+        // word maps: a sentinel bit "SSE n1" above the last one (their masks always have room for it) whose map element
+        // holds "unmapped", so the upper neighbour always exists and the empty case needs no select
+        uint32_t ms[W1];
+#pragma unroll
+        for (int w = 0; w < W1; w++) ms[w] = mq[w] | bit_in_word(v.n1, w);
+        hi = LiveMap::get(v.smap, low_at_or_above<W1>(ms, i + 1), v.mstride);
+      } else {
+        const int kn = low_at_or_above<W1>(mq, i + 1);            // -1 for the last query SSE: nothing above it
+        hi = kn >= 0 ? LiveMap::get(v.smap, kn, v.mstride) : -1;
+      }
       if (i == v.n1 - 1) hi = v.n2;
     } else {
       lo = 0; hi = v.n2;
@@ -513,7 +522,10 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
 #pragma unroll
     for (int w = 0; w < W2; w++) asm volatile("st.shared.b32 [%0], %1;" ::"r"(v.qmask + (uint32_t)(k * W2 + w) * 4u), "r"(tm[w]) : "memory");
   }
-  if (W1 <= 2) Map<true>::put(v.smap, -1, v.mstride, v.n2);       // see Chain::move: the lower window bound of "nothing mapped below"
+  if (W1 <= 2) {                                                   // see Chain::move: the window bounds of "nothing mapped below / above"
+    Map<true>::put(v.smap, -1, v.mstride, v.n2);
+    Map<true>::put(v.smap, v.n1, v.mstride, -1);
+  }
   __syncwarp();
   Chain<W1, W2, LORDER, XORWOW, LSOLN> ch;
   int best = SATS_K_NEG_INIT;
