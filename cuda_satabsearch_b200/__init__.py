@@ -69,6 +69,7 @@ def _load() -> C.CDLL:
         "sats_searcher_launch_count": (C.c_longlong, [vp]),
         "sats_searcher_get_xorwow": (ci, [vp, vp]), "sats_searcher_reset_xorwow": (ci, [vp, C.c_uint64]),
         "sats_device_count": (ci, []),
+        "sats_score_threshold": (C.c_int32, [C.c_double, ci, ci]),
         "sats_search_topk": (ci, [vp, ci, vp, vp]),
         "sats_search_hits": (ci, [vp, C.c_double, ci, vp, vp, vp]),
         "sats_results_parse": (ci, [cs, C.c_size_t, P(vp)]), "sats_results_free": (None, [vp]),
@@ -350,6 +351,11 @@ class Searcher:
 
     def reset_xorwow(self, seed: int = 1234):
         _check(lib().sats_searcher_reset_xorwow(self._h, seed))
+
+
+def score_threshold(z_min: float, n1: int, n2: int) -> int:
+    """Smallest raw score whose printed z-score reaches z_min for sizes (n1, n2); 2**31 - 1 if none does."""
+    return int(lib().sats_score_threshold(float(z_min), n1, n2))
 
 
 def parse_results(text: bytes | str):

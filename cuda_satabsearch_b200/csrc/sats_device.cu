@@ -845,18 +845,10 @@ extern "C" int sats_search_hits(sats_searcher *s, double z_min, int cap, int32_t
   CK(cudaSetDevice(s->device));
   const int D = (int)s->sorted_orig.size(), Q = s->last_q, T = SATS_MAXDIM_EXT + 1;
   const int kcap = std::min(cap, std::max(1, D));      // rows the device keeps per query; the caller's rows stay `cap` wide
-  // z is a non-decreasing step function of the raw score for fixed sizes (norm2 = 2 score / (n1 + n2), truncated to int
-  // at the z_gumbel call like the reference does): bisect for the first score that passes.  |score| <= 2 C(111, 2) = 12210.
-  const int kLo = -16384, kHi = 16384;
+  // one integer score threshold per (query slot, structure order): see sats_score_threshold()
   std::vector<int32_t> thr((size_t)Q * T);
   for (int q = 0; q < Q; q++)
-    for (int n2 = 0; n2 < T; n2++) {
-      auto pass = [&](int sc) { return sats_z_gumbel((int)sats_norm2(sc, s->q_n1[q], n2), sats_gumbel_a, sats_gumbel_b) >= z_min; };
-      int lo = kLo, hi = kHi;
-      if (n2 == 0 || !pass(hi)) { thr[(size_t)q * T + n2] = INT_MAX; continue; }
-      while (lo < hi) { int mid = lo + (hi - lo) / 2; if (pass(mid)) hi = mid; else lo = mid + 1; }
-      thr[(size_t)q * T + n2] = lo;
-    }
+    for (int n2 = 0; n2 < T; n2++) thr[(size_t)q * T + n2] = n2 == 0 ? INT_MAX : sats_score_threshold(z_min, s->q_n1[q], n2);
   // device / pinned buffer: [Q counts][Q bases][cursor][pad][thresholds Q x T][pairs: int2 x Q x cap]
   const size_t head = 2 * (size_t)Q + 2, pair_off = (head + thr.size() + 1) & ~(size_t)1, words = pair_off + 2 * (size_t)Q * kcap;
   if (words > s->hits_cap) {

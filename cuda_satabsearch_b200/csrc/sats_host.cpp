@@ -480,6 +480,21 @@ extern "C" double sats_z_gumbel(int x, double a, double b)
 
 extern "C" double sats_pv_gumbel(double z) { return 1 - exp(-exp(-((M_PI / sqrt(6.0)) * z + kEulerGamma))); }
 
+// z is a non-decreasing step function of the raw score for fixed sizes (norm2 = 2 score / (n1 + n2), truncated to int at the
+// z_gumbel call like the reference does): bisect for the first score that passes.  |score| <= 2 C(111, 2) = 12210.
+extern "C" int32_t sats_score_threshold(double z_min, int size1, int size2)
+{
+  auto pass = [&](int sc) { return sats_z_gumbel((int)sats_norm2(sc, size1, size2), sats_gumbel_a, sats_gumbel_b) >= z_min; };
+  int lo = -16384, hi = 16384;
+  if (!(z_min == z_min) || size1 + size2 < 1 || !pass(hi)) return INT32_MAX;
+  while (lo < hi) {
+    int mid = lo + (hi - lo) / 2;
+    if (pass(mid)) hi = mid;
+    else lo = mid + 1;
+  }
+  return lo;
+}
+
 extern "C" size_t sats_format_block(char *buf, size_t cap, const char *query_id, int query_order, const char *dbfile,
                                     int lorder, int lsoln, const sats_db *db, const int32_t *index, int count,
                                     const int32_t *scores, const int32_t *maps)

@@ -106,6 +106,9 @@ extern const double sats_gumbel_b;   /* gumbelstats.h:28 */
 double sats_norm2(int score, int size1, int size2);        /* gumbelstats.c:91 */
 double sats_z_gumbel(int x, double a, double b);           /* gumbelstats.c:50 (int x: truncation!) */
 double sats_pv_gumbel(double z);                           /* gumbelstats.c:69 */
+/* The smallest raw score whose printed z-score (z_gumbel of the int-truncated norm2, as in cudaSaTabsearch.cu:447-450) reaches
+ * z_min for a query of size1 and a structure of size2 SSEs; INT32_MAX if no score can.  sats_search_hits() cuts with it.  */
+int32_t sats_score_threshold(double z_min, int size1, int size2);
 
 /* Result block printer = cudaSaTabsearch.cu:415-420 + 442-454 for one (query, pool): three '#'
  * header lines, then "%-8s %d %g %g %g" rows (+ "%3d %3d" map pairs if lsoln).  `index` lists the

@@ -208,3 +208,17 @@ def test_c_consumer_links_and_runs(tmp_path):
     assert first[:2] == ["586", "67"] and abs(float(first[2]) - 6.75) < 1e-9 and abs(float(first[3]) - 11.7853) < 1e-3
     if S.device_count() == 0:
         assert "no CUDA device" in p.stdout
+
+
+def test_score_threshold_is_the_first_score_that_passes():
+    """sats_score_threshold (the cut sats_search_hits applies on the device) against the printer's own z-score formula."""
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        n1, n2 = int(rng.integers(1, 112)), int(rng.integers(1, 129))
+        z = float(rng.uniform(-3.0, 40.0))
+        t = S.score_threshold(z, n1, n2)
+        if t == 2**31 - 1:
+            assert stats(16384, n1, n2)[1] < z
+            continue
+        assert stats(t, n1, n2)[1] >= z and stats(t - 1, n1, n2)[1] < z, (n1, n2, z, t)
+    assert S.score_threshold(-1e9, 5, 7) == -16384 and S.score_threshold(float("nan"), 5, 7) == 2**31 - 1
