@@ -105,6 +105,23 @@ int tableau_code(char c0, char c1, int *out)
   return 0;
 }
 
+inline bool is_digit(char ch) { return ch >= '0' && ch <= '9'; }
+
+// strtof("dd.ddd") for all 100 000 texts the "%6.3f" format can produce below 100, indexed by the five digits
+const float *canonical_distances()
+{
+  static const std::vector<float> table = [] {
+    std::vector<float> t(100000);
+    char buf[16];
+    for (int k = 0; k < 100000; k++) {
+      snprintf(buf, sizeof buf, "%d.%03d", k / 1000, k % 1000);
+      t[(size_t)k] = strtof(buf, nullptr);
+    }
+    return t;
+  }();
+  return table.data();
+}
+
 // header token pair "%8s %d": a name of at most 8 characters, then the order
 bool read_header(Cursor &c, char name[9], int *order)
 {
@@ -161,6 +178,7 @@ int parse_entries(Cursor &c, const char *what, sats_db *db, int max_order = SATS
       }
     }
     char field[64];
+    const float *canon = canonical_distances();
     for (int i = 0; i < n; i++) {
       if (!c.line(b, e)) return sats_fail(SATS_ERR_PARSE, "%s structure %s: truncated distance matrix (row %d of %d)", what, name, i + 1, n);
       if (!keep) continue;
@@ -169,6 +187,14 @@ int parse_entries(Cursor &c, const char *what, sats_db *db, int max_order = SATS
         // cannot continue a number (so a wider value bleeds into the next field, as in the reference)
         const char *s = b + 7 * j;
         if (s >= e) return sats_fail(SATS_ERR_PARSE, "%s structure %s: distance row %d too short", what, name, i + 1);
+        // the writer's own "%6.3f " shape -- "[ d]d.ddd" and then something that ends the number: what strtof returns for
+        // it was tabulated once (with strtof), so this is the same float without the call
+        if (e - s >= 6 && s[2] == '.' && (s[0] == ' ' || is_digit(s[0])) && is_digit(s[1]) && is_digit(s[3]) && is_digit(s[4]) &&
+            is_digit(s[5]) && (e - s == 6 || s[6] == ' ' || s[6] == '\t' || s[6] == '\r')) {
+          const int k = (s[0] == ' ' ? 0 : (s[0] - '0') * 10000) + (s[1] - '0') * 1000 + (s[3] - '0') * 100 + (s[4] - '0') * 10 + (s[5] - '0');
+          tdm[(size_t)i * (i + 1) / 2 + j] = canon[k];
+          continue;
+        }
         size_t len = std::min((size_t)(e - s), sizeof field - 1);
         memcpy(field, s, len);
         field[len] = 0;
@@ -375,6 +401,33 @@ extern "C" int sats_db_bootstrap(const sats_db *src, int count, uint64_t seed, i
 }
 
 // ------------------------------------------------------------------------------------------ writers
+// "%6.3f " of a distance without going through printf.  A float times 1000 is exact in double (24 + 10 significant bits),
+// so nearbyint() of it is the round-half-even of the exact value -- what printf prints.  Anything that does not fit
+// "dd.ddd" (negative, -0, >= 99.9995, non-finite) takes the printf route.
+static inline void put_distance(std::string &out, float d)
+{
+  double v = std::isnan(d) ? 0.0 : (double)d;      // convdb2.py: NaN -> 0.000
+  if (!std::signbit(v) && v < 99.9995) {
+    const long k = std::lrint(v * 1000.0);         // default rounding mode: to nearest, ties to even
+    if (k <= 99999) {
+      char buf[7];
+      const int ip = (int)(k / 1000), fp = (int)(k % 1000);
+      buf[0] = ip >= 10 ? (char)('0' + ip / 10) : ' ';
+      buf[1] = (char)('0' + ip % 10);
+      buf[2] = '.';
+      buf[3] = (char)('0' + fp / 100);
+      buf[4] = (char)('0' + fp / 10 % 10);
+      buf[5] = (char)('0' + fp % 10);
+      buf[6] = ' ';
+      out.append(buf, 7);
+      return;
+    }
+  }
+  char buf[64];
+  int n = snprintf(buf, sizeof buf, "%6.3f ", v);
+  out.append(buf, (size_t)n);
+}
+
 extern "C" int sats_db_write_ascii(const sats_db *db, const char *path)
 {
   if (!db || !path) return sats_fail(SATS_ERR_ARG, "sats_db_write_ascii: null argument");
@@ -382,25 +435,26 @@ extern "C" int sats_db_write_ascii(const sats_db *db, const char *path)
   if (!fp) return sats_fail(SATS_ERR_IO, "cannot open %s for writing", path);
   static const char HI[] = "PROL?", LO[] = "EDST?";
   static const char *TY[] = {"e ", "xa", "xi", "xg"};
+  std::string out;
+  char head[64];
   for (int e = 0; e < db->count(); e++) {
     int n = db->order[e];
-    if (e) fputc('\n', fp);
-    fprintf(fp, "%6s %4d\n", db->name(e), n);
+    out.clear();
+    if (e) out.push_back('\n');
+    out.append(head, (size_t)snprintf(head, sizeof head, "%6s %4d\n", db->name(e), n));
     for (int i = 0; i < n; i++) {
       for (int j = 0; j <= i; j++) {
         uint8_t v = db->code(e, i, j);
-        if (i == j) fprintf(fp, "%s ", TY[v & 3]);
-        else fprintf(fp, "%c%c ", HI[std::min(v >> 4, 4)], LO[std::min(v & 15, 4)]);
+        if (i == j) { out.append(TY[v & 3], 2); out.push_back(' '); }
+        else { out.push_back(HI[std::min(v >> 4, 4)]); out.push_back(LO[std::min(v & 15, 4)]); out.push_back(' '); }
       }
-      fputc('\n', fp);
+      out.push_back('\n');
     }
     for (int i = 0; i < n; i++) {
-      for (int j = 0; j <= i; j++) {
-        float d = db->dist(e, i, j);
-        fprintf(fp, "%6.3f ", std::isnan(d) ? 0.0 : (double)d);      // convdb2.py: NaN -> 0.000
-      }
-      fputc('\n', fp);
+      for (int j = 0; j <= i; j++) put_distance(out, db->dist(e, i, j));
+      out.push_back('\n');
     }
+    if (fwrite(out.data(), 1, out.size(), fp) != out.size()) { fclose(fp); return sats_fail(SATS_ERR_IO, "write error on %s", path); }
   }
   if (fclose(fp)) return sats_fail(SATS_ERR_IO, "write error on %s", path);
   return SATS_OK;

@@ -222,3 +222,16 @@ def test_score_threshold_is_the_first_score_that_passes():
             continue
         assert stats(t, n1, n2)[1] >= z and stats(t - 1, n1, n2)[1] < z, (n1, n2, z, t)
     assert S.score_threshold(-1e9, 5, 7) == -16384 and S.score_threshold(float("nan"), 5, 7) == 2**31 - 1
+
+
+def test_fast_distance_parse_equals_strtof_for_every_canonical_value():
+    """The parser reads the writer's "%6.3f" fields through a table of strtof results; a trailing zero pushes the same
+    values through strtof itself.  All 100 000 of them must agree bit for bit."""
+    fast = "".join("s%05d     1\ne  \n%6.3f \n\n" % (k % 100000, k / 1000.0) for k in range(100000))
+    slow = "".join("s%05d     1\ne  \n%d.%03d0 \n\n" % (k % 100000, k // 1000, k % 1000) for k in range(100000))
+    a, b = S.Database.parse_ascii(fast), S.Database.parse_ascii(slow)
+    assert len(a) == len(b) == 100000
+    va = np.array([a.get(i)[1][0, 0] for i in range(100000)], np.float32)
+    vb = np.array([b.get(i)[1][0, 0] for i in range(100000)], np.float32)
+    assert np.array_equal(va.view(np.uint32), vb.view(np.uint32))
+    assert abs(float(va[-1]) - 99.999) < 1e-5 and (np.diff(va) > 0).all()

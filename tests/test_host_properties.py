@@ -54,3 +54,39 @@ def test_formatter_and_reader_are_inverse(scores, qn, lorder):
     assert blk[0]["names"] == names and blk[0]["scores"].tolist() == scores
     for k in range(n):
         assert abs(blk[0]["norm2"][k] - S.norm2(scores[k], qn, 1 + k % 7)) <= 1e-5 * max(1.0, abs(blk[0]["norm2"][k]))
+
+
+def test_ascii_writer_formats_distances_like_printf(tmp_path):
+    """The writer's hand-rolled "%6.3f " must equal printf's for every float: exact ties at the third decimal (round half
+    to even), the 99.9995 boundary, values that need more than six characters, negatives, -0, NaN (-> 0.000), random bit
+    patterns."""
+    rng = np.random.default_rng(99)
+    vals = [0.0, -0.0, 0.0005, 0.0015, 0.0625, 0.1875, 0.3125, 2.5e-4, 9.9995, 9.99949, 99.9994, 99.9995, 99.99951, 100.0, 123.456,
+            1e6, -1.0, -0.0004, -12.3456, float("nan"), 1e-30, 5e-4, 1.0005, 31.4155, 31.4165, 64.0625, 7.8125e-3]
+    vals += [k / 1000.0 + 0.0005 for k in range(0, 4000, 37)]                    # near-ties as doubles -> float
+    vals += [float(x) for x in rng.uniform(0, 100, 3000)]
+    vals += [float(np.frombuffer(np.uint32(b).tobytes(), np.float32)[0]) for b in rng.integers(0x30000000, 0x42C80000, 3000)]
+    vals = np.array(vals, np.float32)
+    n = 111
+    per = n * (n - 1) // 2
+    structs = []
+    for s in range(0, len(vals), per):
+        chunk = vals[s:s + per]
+        dm = np.zeros((n, n), np.float32)
+        iu = np.tril_indices(n, -1)
+        dm[iu[0][:len(chunk)], iu[1][:len(chunk)]] = chunk
+        dm = dm + dm.T
+        structs.append(("w%05d" % s, np.zeros((n, n), np.uint8), dm))
+    db = S.Database.from_structures([x[0] for x in structs], [x[1] for x in structs], [x[2] for x in structs])
+    db.write_ascii(tmp_path / "w.ascii")
+    lines = (tmp_path / "w.ascii").read_text().split("\n")
+    pos = 0
+    for name, _, dm in structs:
+        while not lines[pos].strip():
+            pos += 1
+        assert lines[pos].split()[0] == name
+        pos += 1 + n                                                              # header + tableau rows
+        for i in range(n):
+            want = "".join("%6.3f " % (0.0 if np.isnan(dm[i, j]) else float(dm[i, j])) for j in range(i + 1))
+            assert lines[pos + i] == want, (name, i)
+        pos += n
