@@ -69,6 +69,7 @@ def _load() -> C.CDLL:
         "sats_searcher_launch_count": (C.c_longlong, [vp]),
         "sats_searcher_get_xorwow": (ci, [vp, vp]), "sats_searcher_reset_xorwow": (ci, [vp, C.c_uint64]),
         "sats_device_count": (ci, []),
+        "sats_pick_boundaries": (ci, [ci, vp]), "sats_accept_cutoffs": (ci, [vp, vp]), "sats_seed_cutoff": (C.c_uint32, []),
         "sats_score_threshold": (C.c_int32, [C.c_double, ci, ci]),
         "sats_search_topk": (ci, [vp, ci, vp, vp]),
         "sats_search_hits": (ci, [vp, C.c_double, ci, vp, vp, vp]),
@@ -265,6 +266,15 @@ def device_count() -> int:
     return lib().sats_device_count()
 
 
+def _out_array(a: np.ndarray, shape, what: str) -> np.ndarray:
+    """A caller-supplied output buffer goes to the C ABI as a bare pointer: it must be exactly what the library writes."""
+    if not isinstance(a, np.ndarray) or a.dtype != np.int32 or not a.flags.c_contiguous or not a.flags.writeable \
+            or tuple(a.shape) != tuple(shape):
+        raise SatsError(f"{what} must be a writable C-contiguous int32 array of shape {tuple(shape)}, got "
+                        f"{getattr(a, 'dtype', type(a))} {getattr(a, 'shape', '')}")
+    return a
+
+
 class Searcher:
     """One GPU's resident copy of (a shard of) a database plus the search entry points."""
 
@@ -299,6 +309,9 @@ class Searcher:
             scores = np.full((qcount, self.count), np.iinfo(np.int32).min, np.int32)
         if p.lsoln and maps is None:
             maps = np.full((qcount, self.count, MAP_STRIDE), -1, np.int32)
+        _out_array(scores, (qcount, self.count), "scores")
+        if p.lsoln:
+            _out_array(maps, (qcount, self.count, MAP_STRIDE), "maps")
         _check(lib().sats_search(self._h, queries._h, qfirst, qcount, C.byref(p), query_index_base,
                                  scores.ctypes.data, maps.ctypes.data if p.lsoln else None))
         return scores, (maps if p.lsoln else None)
@@ -320,6 +333,9 @@ class Searcher:
             scores = np.full((q, self.count), np.iinfo(np.int32).min, np.int32)
         if self._lsoln and maps is None:
             maps = np.full((q, self.count, MAP_STRIDE), -1, np.int32)
+        _out_array(scores, (q, self.count), "scores")
+        if self._lsoln:
+            _out_array(maps, (q, self.count, MAP_STRIDE), "maps")
         _check(lib().sats_search_collect(self._h, scores.ctypes.data, maps.ctypes.data if self._lsoln else None))
         return scores, (maps if self._lsoln else None)
 
@@ -353,6 +369,25 @@ class Searcher:
         _check(lib().sats_searcher_reset_xorwow(self._h, seed))
 
 
+def pick_boundaries(n: int) -> np.ndarray:
+    """cut[k] = smallest 32-bit draw whose SSE pick among n is >= k (validation aid, see include/sats.h)."""
+    cut = np.zeros(n, np.uint32)
+    _check(lib().sats_pick_boundaries(n, cut.ctypes.data))
+    return cut
+
+
+def accept_cutoffs():
+    """-> (cut uint32 [100, 230], temps float32 [100]): the Metropolis test as integer cut-offs (validation aid)."""
+    cut = np.zeros((100, 230), np.uint32)
+    temps = np.zeros(100, np.float32)
+    _check(lib().sats_accept_cutoffs(cut.ctypes.data, temps.ctypes.data))
+    return cut, temps
+
+
+def seed_cutoff() -> int:
+    return int(lib().sats_seed_cutoff())
+
+
 def score_threshold(z_min: float, n1: int, n2: int) -> int:
     """Smallest raw score whose printed z-score reaches z_min for sizes (n1, n2); 2**31 - 1 if none does."""
     return int(lib().sats_score_threshold(float(z_min), n1, n2))
@@ -374,12 +409,13 @@ def parse_results(text: bytes | str):
                        scores=np.zeros(n, np.int32), norm2=np.zeros(n), z=np.zeros(n), p=np.zeros(n), maps=[])
             name = C.create_string_buffer(9)
             sc = C.c_int32(); a = C.c_double(); z = C.c_double(); p = C.c_double()
-            pairs = np.zeros(2 * MAXDIM, np.int32)
+            cap = MAXDIM_EXT
+            pairs = np.zeros(2 * cap, np.int32)
             for r in range(n):
                 lib().sats_results_row(h, k, r, name, C.byref(sc), C.byref(a), C.byref(z), C.byref(p))
                 blk["names"].append(name.value.decode())
                 blk["scores"][r], blk["norm2"][r], blk["z"][r], blk["p"][r] = sc.value, a.value, z.value, p.value
-                m = lib().sats_results_map(h, k, r, pairs.ctypes.data, MAXDIM)
+                m = min(max(lib().sats_results_map(h, k, r, pairs.ctypes.data, cap), 0), cap)     # malformed input may list more
                 blk["maps"].append(pairs[:2 * m].reshape(m, 2).copy())
             out.append(blk)
     finally:

@@ -13,8 +13,9 @@
  * Differences, all deliberate: -c is refused (this build has no CPU search path); -q computes norm2 with the
  * query's own order like the reference's CPU branch (:366, :380) rather than the GPU branch's orders[qi]
  * (:996-998); the db file may also be a packed SATSDB1 cache.  Extra options:
- *   -g N      N cost-weighted shards of the size-sorted db, one per GPU (shards share devices when N exceeds the GPUs
- *             present); Philox mode only
+ *   -g N      N GPUs (devices are shared when N exceeds the GPUs present).  Philox: N cost-weighted shards of the
+ *             size-sorted db.  xorwow: the db is replicated and GPU g runs the reference blocks b with b % N == g
+ *             (cudaSaTabsearch_kernel.cu:932), so the output equals the single-GPU validation run
  *   -R mode   philox (default) | xorwow  -- xorwow = the reference GPU run's 128x128 cuRAND streams
  *   -A mode   table (default) | fast     -- Metropolis thresholds: host libm table | device fast-math
  *   -s seed   RNG seed (default 1234)
@@ -140,8 +141,9 @@ int main(int argc, char *argv[])
   }
   if (maxstart < 1) { fprintf(stderr, "ERROR: restarts must be >= 1\n"); exit(1); }
   if (ngpus < 1 || ngpus > MAX_GPUS) { fprintf(stderr, "ERROR: -g must be 1..%d\n", MAX_GPUS); exit(1); }
-  if (ngpus > 1 && rng_mode == SATS_RNG_XORWOW_GRID) {
-    fprintf(stderr, "ERROR: -R xorwow reproduces a single-GPU reference run; use -g 1\n");
+  const int split_blocks = ngpus > 1 && rng_mode == SATS_RNG_XORWOW_GRID;      /* replicate the db, split the reference blocks */
+  if (accept_mode == SATS_ACCEPT_DEVICE_FAST && rng_mode != SATS_RNG_XORWOW_GRID) {
+    fprintf(stderr, "ERROR: -A fast (the reference GPU build's fast-math acceptance) goes with -R xorwow\n");
     exit(1);
   }
   if (topk < 0) { fprintf(stderr, "ERROR: -k needs a positive count\n"); exit(1); }
@@ -210,7 +212,7 @@ int main(int argc, char *argv[])
   t0 = now_ms();
   sats_searcher *sr[MAX_GPUS];
   for (int g = 0; g < ngpus; g++)
-    if (sats_searcher_create(db, g % have, g, ngpus, &sr[g]) != SATS_OK) die("ERROR creating searcher");
+    if (sats_searcher_create(db, g % have, split_blocks ? 0 : g, split_blocks ? 1 : ngpus, &sr[g]) != SATS_OK) die("ERROR creating searcher");
   fprintf(stderr, "Copied %d entries to %d GPU(s) in %f ms\n", dbsize, ngpus, now_ms() - t0);
 
   sats_params prm;
@@ -240,8 +242,10 @@ int main(int argc, char *argv[])
       double t1 = now_ms();
       for (int g = 0; g < ngpus; g++)
         if (sats_search_upload(sr[g], queries, q0, nq) != SATS_OK) die("ERROR uploading queries");
-      for (int g = 0; g < ngpus; g++)
+      for (int g = 0; g < ngpus; g++) {
+        if (split_blocks) { prm.grid_rank = g; prm.grid_count = ngpus; }
         if (sats_search_launch(sr[g], &prm, (uint32_t)q0, NULL) != SATS_OK) die("kernel launch failed");
+      }
       /* hits-only modes: hcap rows per query come back from the device instead of one score per database entry */
       const int hits_only = topk > 0 || zcut;
       const int hcap = topk > 0 ? topk : (n > 0 ? n : 1);

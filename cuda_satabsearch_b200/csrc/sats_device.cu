@@ -41,6 +41,64 @@ __global__ void sats_xorwow_init_kernel(uint32_t *states, int n, unsigned long l
   for (int k = 0; k < 5; k++) o[1 + k] = st.v[k];
 }
 
+// ---- integer forms of the reference's decisions on a uniform --------------------------------------------------------
+// The reference turns 32 random bits x into u = unit(x) in (0, 1] (curand_uniform) and then decides with fp32 / fp64
+// arithmetic.  unit() is monotone in x, so every such decision is "x < cut" for a cut-off that bisection finds with the
+// reference's own expressions; the kernel then compares integers and never converts a draw.
+static float unit_from_bits(uint32_t x) { return (float)x * 2.3283064e-10f + 1.1641532e-10f; }     // curand_uniform.h:69-72
+// (int)((u - 1.1e-7) * n) in double (cudaSaTabsearch_kernel.cu:67, :1042)
+static int pick_from_bits(uint32_t x, int n) { return (int)(((double)unit_from_bits(x) - 1.1e-7) * (double)n); }
+// smallest x in [0, 2^32) with pred(x) true, for a predicate that is monotone (false ... false true ... true); 0 if it is
+// true everywhere; *none = true (and 0xffffffff returned) if it is false everywhere
+template <class Pred> static uint32_t first_true(Pred pred, bool *none = nullptr)
+{
+  if (none) *none = false;
+  if (!pred(0xffffffffu)) { if (none) *none = true; return 0xffffffffu; }
+  uint64_t lo = 0, hi = 0xffffffffull;          // pred(hi) holds
+  while (lo < hi) {
+    const uint64_t mid = lo + (hi - lo) / 2;
+    if (pred((uint32_t)mid)) hi = mid;
+    else lo = mid + 1;
+  }
+  return (uint32_t)lo;
+}
+// pick_cut[k] = smallest x whose SSE pick is >= k, k = 0..n-1 (see pick_index() in sats_kernel.cuh)
+extern "C" int sats_pick_boundaries(int n, uint32_t *cut)
+{
+  if (n < 1 || n > SATS_MAXDIM_EXT || !cut) return sats_fail(SATS_ERR_ARG, "sats_pick_boundaries: bad argument");
+  for (int k = 0; k < n; k++) {
+    bool none;
+    cut[k] = first_true([&](uint32_t x) { return pick_from_bits(x, n) >= k; }, &none);
+    // the kernel starts from umulhi(x, n) and steps down by at most one: both must bracket the exact boundary
+    const uint64_t naive = (((uint64_t)k << 32) + (uint64_t)n - 1) / (uint64_t)n;       // smallest x with umulhi(x, n) >= k
+    const uint64_t next = (((uint64_t)(k + 1) << 32) + (uint64_t)n - 1) / (uint64_t)n;
+    if (none || cut[k] < naive || (uint64_t)cut[k] >= next)
+      return sats_fail(SATS_ERR_ARG, "sats_pick_boundaries: boundary %d of %d outside its multiply-high step", k, n);
+  }
+  return SATS_OK;
+}
+// cut[m][nd], m = 0..99, nd = 0..229: a move of score change -nd at step m is accepted iff x < cut, i.e. iff
+// expf((float)(-nd) / T_m) > unit(x) with T_0 = 10, T <- 0.95f T in fp32 (cudaSaTabsearch_kernel.cu:1030, :1166, :1189)
+extern "C" int sats_accept_cutoffs(uint32_t *cut, float *temps)
+{
+  if (!cut) return sats_fail(SATS_ERR_ARG, "sats_accept_cutoffs: null argument");
+  float t = 10.0f;
+  for (int m = 0; m < SATS_K_MOVES; m++) {
+    if (temps) temps[m] = t;
+    for (int nd = 0; nd <= SATS_K_DCLAMP; nd++) {
+      const float thr = expf((float)(-nd) / t);
+      bool none;
+      const uint32_t c = first_true([&](uint32_t x) { return !(thr > unit_from_bits(x)); }, &none);
+      if (none) return sats_fail(SATS_ERR_ARG, "sats_accept_cutoffs: threshold %g above every uniform", (double)thr);
+      cut[(size_t)m * (SATS_K_DCLAMP + 1) + nd] = c;
+    }
+    t *= 0.95f;
+  }
+  return SATS_OK;
+}
+// the seeding pass attempts a match iff unit(x) < 0.5 (INIT_MATCHPROB, saparams.h:43; kernel.cu:624)
+extern "C" uint32_t sats_seed_cutoff(void) { return first_true([](uint32_t x) { return !((double)unit_from_bits(x) < 0.5); }); }
+
 typedef sats_kernel_fn kernel_fn;
 // one kernel launch of a search, as planned on the host
 struct LaunchDesc {
@@ -61,13 +119,15 @@ struct sats_searcher {
   cudaEvent_t side_done[kSide] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t fork = nullptr;
   int db_count = 0;                       // entries of the whole database (output indexing)
+  int shard_count = 1;                    // > 1: this searcher holds one part of sats_partition()
   std::vector<int32_t> sorted_orig;       // local sorted position -> original db index (decreasing order)
   std::vector<int32_t> sorted_order;
   std::vector<int32_t> file_rank;         // local sorted position -> rank in original file order among local entries
   uint8_t *d_blobs = nullptr;
   uint64_t *d_blob_off = nullptr;
   uint32_t *d_blob_bytes = nullptr;
-  float *d_accept = nullptr;
+  uint32_t *d_accept = nullptr;          // Metropolis cut-offs [moves][230], then the fp32 temperature schedule [moves]
+  uint32_t accept_cut0 = 0, seed_cut = 0;
   uint32_t *d_xw = nullptr;
   bool xw_ready = false;
   uint64_t xw_seed = 0;
@@ -82,6 +142,8 @@ struct sats_searcher {
   cudaGraphExec_t graph_exec = nullptr;   // launch shape per (kernel variant, shared-memory sizes)
   int *d_counters = nullptr; size_t counter_cap = 0;   // one work counter per (bucket launch, query) of a search
   // queries
+  std::array<std::array<uint32_t, SATS_MAXDIM + 1>, SATS_MAXDIM + 1> pick_cut;      // [n1]: SSE-pick boundaries, built on first use
+  std::array<bool, SATS_MAXDIM + 1> pick_cut_ready{};
   uint8_t *d_qblobs = nullptr; size_t qblob_cap = 0;
   uint64_t *d_qoff = nullptr; uint32_t *d_qbytes = nullptr; int qmeta_cap = 0;
   uint8_t *h_qstage = nullptr; size_t h_qstage_cap = 0;
@@ -90,7 +152,6 @@ struct sats_searcher {
   std::vector<int> q_n1;               // by slot
   std::vector<uint32_t> q_bytes;       // by slot
   std::vector<int> slot_q;
-  int32_t *d_qorig = nullptr;          // by slot: position in the batch (keys the Philox streams)
   // results
   int32_t *d_scores = nullptr; int8_t *d_maps = nullptr;
   int32_t *h_scores = nullptr; int8_t *h_maps = nullptr;
@@ -150,7 +211,7 @@ extern "C" int sats_device_count(void)
 }
 
 extern "C" int sats_searcher_create(const sats_db *db, int device, int shard_rank, int shard_count, sats_searcher **out)
-{
+try {
   if (!db || !out) return sats_fail(SATS_ERR_ARG, "sats_searcher_create: null argument");
   if (shard_count < 1) shard_count = 1;
   if (shard_rank < 0 || shard_rank >= shard_count) return sats_fail(SATS_ERR_ARG, "bad shard %d of %d", shard_rank, shard_count);
@@ -166,6 +227,7 @@ extern "C" int sats_searcher_create(const sats_db *db, int device, int shard_ran
   s->device = device;
   s->num_sms = prop.multiProcessorCount;
   s->db_count = db->count();
+  s->shard_count = shard_count;
   std::vector<int32_t> owner((size_t)db->count(), 0);
   if (shard_count > 1) sats_partition(db, shard_count, owner.data());
   std::vector<int32_t> local;
@@ -221,15 +283,15 @@ extern "C" int sats_searcher_create(const sats_db *db, int device, int shard_ran
     CKF(cudaMemcpy(s->d_blob_bytes, bytes.data(), local.size() * 4, cudaMemcpyHostToDevice));
     CKF(cudaMemcpy(s->d_sorted_order, s->sorted_order.data(), local.size() * 4, cudaMemcpyHostToDevice));
   }
-  // Metropolis thresholds and temperatures exactly as the reference's host path evaluates them
-  std::vector<float> temps(SATS_K_MOVES), tab((size_t)SATS_K_MOVES * (SATS_K_DCLAMP + 1));
-  float t = 10.0f;
-  for (int m = 0; m < SATS_K_MOVES; m++) {
-    temps[m] = t;
-    for (int d = 0; d <= SATS_K_DCLAMP; d++) tab[(size_t)m * (SATS_K_DCLAMP + 1) + d] = expf((float)(-d) / t);
-    t *= 0.95f;
-  }
-  CKF(cudaMalloc(&s->d_accept, (tab.size() + temps.size()) * 4));      // thresholds, then the temperature schedule
+  // Metropolis cut-offs and temperatures exactly as the reference's host path evaluates them
+  std::vector<float> temps(SATS_K_MOVES);
+  std::vector<uint32_t> tab((size_t)SATS_K_MOVES * (SATS_K_DCLAMP + 1));
+  if (sats_accept_cutoffs(tab.data(), temps.data()) != SATS_OK) return fail(SATS_ERR_ARG);
+  s->accept_cut0 = tab[0];                                                // d == 0: expf(0) = 1 at every step
+  for (int m = 0; m < SATS_K_MOVES; m++)
+    if (tab[(size_t)m * (SATS_K_DCLAMP + 1)] != s->accept_cut0) return fail(sats_fail(SATS_ERR_ARG, "accept cut-off for d = 0 varies"));
+  s->seed_cut = sats_seed_cutoff();
+  CKF(cudaMalloc(&s->d_accept, (tab.size() + temps.size()) * 4));      // cut-offs, then the temperature schedule
   CKF(cudaMemcpy(s->d_accept, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
   CKF(cudaMemcpy(s->d_accept + tab.size(), temps.data(), temps.size() * 4, cudaMemcpyHostToDevice));
   CKF(cudaMalloc(&s->d_xw, (size_t)SATS_REF_GRID_BLOCKS * SATS_REF_GRID_THREADS * 6 * 4));
@@ -237,6 +299,7 @@ extern "C" int sats_searcher_create(const sats_db *db, int device, int shard_ran
   *out = s;
   return SATS_OK;
 }
+SATS_CATCH_ALL
 
 extern "C" void sats_searcher_free(sats_searcher *s)
 {
@@ -244,7 +307,7 @@ extern "C" void sats_searcher_free(sats_searcher *s)
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
   cudaFree(s->d_blobs); cudaFree(s->d_blob_off); cudaFree(s->d_blob_bytes); cudaFree(s->d_accept); cudaFree(s->d_xw);
-  cudaFree(s->d_pool_list); cudaFree(s->d_xw_blocks); cudaFree(s->d_counters); cudaFree(s->d_qblobs); cudaFree(s->d_qoff); cudaFree(s->d_qbytes); cudaFree(s->d_qorig);
+  cudaFree(s->d_pool_list); cudaFree(s->d_xw_blocks); cudaFree(s->d_counters); cudaFree(s->d_qblobs); cudaFree(s->d_qoff); cudaFree(s->d_qbytes);
   cudaFree(s->d_scores); cudaFree(s->d_maps); cudaFree(s->d_topk); cudaFreeHost(s->h_topk);
   cudaFree(s->d_sorted_order); cudaFree(s->d_hits); cudaFreeHost(s->h_hits);
   if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
@@ -295,7 +358,7 @@ extern "C" int sats_searcher_get_xorwow(sats_searcher *s, uint32_t *states6)
 }
 
 extern "C" int sats_search_upload(sats_searcher *s, const sats_db *queries, int qfirst, int qcount)
-{
+try {
   if (!s || !queries || qcount < 1 || qfirst < 0 || qfirst + qcount > queries->count())
     return sats_fail(SATS_ERR_ARG, "sats_search_upload: bad query range");
   CK(cudaSetDevice(s->device));
@@ -320,7 +383,7 @@ extern "C" int sats_search_upload(sats_searcher *s, const sats_db *queries, int 
     s->q_bytes[slot] = (uint32_t)query_blob_bytes(n);
     total += s->q_bytes[slot];
   }
-  size_t meta = (size_t)qcount * 16;
+  size_t meta = (size_t)qcount * 12;
   if (total + meta > s->h_qstage_cap) {
     cudaFreeHost(s->h_qstage);
     s->h_qstage = nullptr;
@@ -336,39 +399,36 @@ extern "C" int sats_search_upload(sats_searcher *s, const sats_db *queries, int 
     s->qblob_cap = total;
   }
   if (qcount > s->qmeta_cap) {
-    cudaFree(s->d_qoff); cudaFree(s->d_qbytes); cudaFree(s->d_qorig);
-    s->d_qoff = nullptr; s->d_qbytes = nullptr; s->d_qorig = nullptr; s->qmeta_cap = 0;
+    cudaFree(s->d_qoff); cudaFree(s->d_qbytes);
+    s->d_qoff = nullptr; s->d_qbytes = nullptr; s->qmeta_cap = 0;
     CK(cudaMalloc(&s->d_qoff, (size_t)qcount * 8));
     CK(cudaMalloc(&s->d_qbytes, (size_t)qcount * 4));
-    CK(cudaMalloc(&s->d_qorig, (size_t)qcount * 4));
     s->qmeta_cap = qcount;
   }
   memset(s->h_qstage, 0, total);
   for (int slot = 0; slot < qcount; slot++) {
     int e = qfirst + s->slot_q[slot], n = queries->order[e];
     uint8_t *b = s->h_qstage + off[slot];
-    int32_t hdr[4] = {n, 0, 0, 0};     // hdr[1] (Philox query index) is patched at launch via q_index_base
+    int32_t hdr[4] = {n, s->slot_q[slot], 0, 0};     // hdr[1]: position in the batch; + q_index_base = Philox query index
     memcpy(b, hdr, 16);
-    for (int i = 0; i < n; i++) b[16 + i] = queries->code(e, i, i);
+    for (int i = 0; i < n; i++) b[16 + i] = queries->code(e, i, i) & 3;      // SSE type 0..3 (the db constructors reject anything else)
+    if (!s->pick_cut_ready[n]) {
+      int prc = sats_pick_boundaries(n, s->pick_cut[n].data());
+      if (prc) return prc;
+      s->pick_cut_ready[n] = true;
+    }
+    memcpy(b + SATS_K_QUERY_PICK, s->pick_cut[n].data(), (size_t)n * 4);
     fill_cells(queries, e, b + SATS_K_QUERY_HDR);
   }
   memcpy(s->h_qstage + total, off.data(), (size_t)qcount * 8);
   memcpy(s->h_qstage + total + (size_t)qcount * 8, s->q_bytes.data(), (size_t)qcount * 4);
-  memcpy(s->h_qstage + total + (size_t)qcount * 12, s->slot_q.data(), (size_t)qcount * 4);
   CK(cudaMemcpyAsync(s->d_qblobs, s->h_qstage, total, cudaMemcpyHostToDevice, s->stream));
   CK(cudaMemcpyAsync(s->d_qoff, s->h_qstage + total, (size_t)qcount * 8, cudaMemcpyHostToDevice, s->stream));
   CK(cudaMemcpyAsync(s->d_qbytes, s->h_qstage + total + (size_t)qcount * 8, (size_t)qcount * 4, cudaMemcpyHostToDevice, s->stream));
-  CK(cudaMemcpyAsync(s->d_qorig, s->h_qstage + total + (size_t)qcount * 12, (size_t)qcount * 4, cudaMemcpyHostToDevice, s->stream));
   s->last_q = qcount;
   return SATS_OK;
 }
-
-// writes the Philox query index into the device copies of the query headers
-__global__ void sats_patch_query_index(uint8_t *qblobs, const uint64_t *qoff, const int32_t *qorig, int qcount, uint32_t base)
-{
-  int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot < qcount) reinterpret_cast<uint32_t *>(qblobs + qoff[slot])[1] = base + (uint32_t)qorig[slot];
-}
+SATS_CATCH_ALL
 
 static int ensure_results(sats_searcher *s, int qcount, int lsoln)
 {
@@ -408,10 +468,12 @@ static int set_attrs_once(sats_searcher *s)
 static const int kBucketBounds[] = {8, 12, 16, 20, 24, 32, 48, 64, 96, SATS_MAXDIM, SATS_MAXDIM_EXT};
 
 extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint32_t query_index_base, float *elapsed_ms)
-{
+try {
   if (!s || !pp) return sats_fail(SATS_ERR_ARG, "sats_search_launch: null argument");
   if (s->last_q < 1) return sats_fail(SATS_ERR_ARG, "sats_search_launch: no queries uploaded");
   if (pp->restarts < 1) return sats_fail(SATS_ERR_ARG, "restarts must be >= 1");
+  if (pp->accept_mode == SATS_ACCEPT_DEVICE_FAST && pp->rng_mode != SATS_RNG_XORWOW_GRID)
+    return sats_fail(SATS_ERR_ARG, "ACCEPT_DEVICE_FAST exists for same-box parity with the reference GPU binary: use it with XORWOW_GRID");
   CK(cudaSetDevice(s->device));
   int rc = set_attrs_once(s);
   if (rc) return rc;
@@ -425,9 +487,6 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
   s->last_lsoln = pp->lsoln;
   CK(cudaMemsetAsync(s->d_scores, 0x80, (size_t)Q * std::max(1, D) * 4, s->stream));
   if (elapsed_ms) CK(cudaEventRecord(s->ev0, s->stream));
-  sats_patch_query_index<<<(Q + 127) / 128, 128, 0, s->stream>>>(s->d_qblobs, s->d_qoff, s->d_qorig, Q, query_index_base);
-  CK(cudaGetLastError());
-  s->launches++;
 
   // pool -> contiguous range of the (decreasing-order) sorted list
   int first_small = 0;
@@ -442,13 +501,22 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
   k.qblobs = s->d_qblobs; k.qblob_off = s->d_qoff; k.qblob_bytes = s->d_qbytes;
   k.restarts = pp->restarts; k.lsoln = pp->lsoln; k.accept_mode = pp->accept_mode;
   k.seed_lo = (uint32_t)seed; k.seed_hi = (uint32_t)(seed >> 32);
-  k.accept_tab = s->d_accept;
-  k.temps = s->d_accept + (size_t)SATS_K_MOVES * (SATS_K_DCLAMP + 1);
+  k.accept_cut = s->d_accept;
+  k.accept_cut0 = s->accept_cut0;
+  k.seed_cut = s->seed_cut;
+  k.q_index_base = query_index_base;
+  k.temps = reinterpret_cast<const float *>(s->d_accept + (size_t)SATS_K_MOVES * (SATS_K_DCLAMP + 1));
   k.out_scores = s->d_scores; k.out_maps = pp->lsoln ? s->d_maps : nullptr; k.out_stride = std::max(1, D);
   k.xw_states = s->d_xw; k.pool_list = s->d_pool_list; k.xw_blocks = s->d_xw_blocks;
 
   if (r1 > r0) {
     if (xorwow) {
+      // The validation streams belong to reference blocks, and block b walks pool positions b, b + 128, ... of the WHOLE
+      // pool (cudaSaTabsearch_kernel.cu:932): a searcher that holds only a part of the database cannot reproduce that.
+      // Multi-GPU validation runs keep the database replicated and split the blocks (grid_rank / grid_count).
+      if (s->shard_count > 1)
+        return sats_fail(SATS_ERR_ARG, "XORWOW_GRID needs the whole database on the device: create the searcher with shard_count 1 "
+                                       "and split the reference blocks with sats_params.grid_rank / grid_count");
       if (!s->xw_ready || s->xw_seed != seed) { rc = sats_searcher_reset_xorwow(s, seed); if (rc) return rc; }
       // pool positions in original file order (cudaSaTabsearch_kernel.cu:932 walks d_orders[] as loaded)
       std::vector<int32_t> list;
@@ -495,6 +563,8 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
       std::vector<LaunchDesc> plan;
       int tw_max = std::min(128, ((pp->restarts + 31) / 32) * 32);
       if (const char *e = getenv("SATS_TW")) { int t = atoi(e); if (t == 32 || t == 64 || t == 128) tw_max = std::min(tw_max, t); }
+      int teams_cap = SATS_K_MAXTHREADS / 32;
+      if (const char *e = getenv("SATS_TEAMS")) teams_cap = std::max(1, std::min(teams_cap, atoi(e)));
       // runs of consecutive queries with the same mask width share launches (grid.y)
       for (int q0 = 0; q0 < Q;) {
         int q1 = q0 + 1;
@@ -523,7 +593,7 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
           // the choice depends only on the kernel variant and the shared-memory sizes: remember it (the occupancy queries
           // below would otherwise cost a few hundred microseconds of host time per search)
           const std::array<int, 8> cfg_key = {w1, words_for(n2max) * 4 + (pp->lorder != 0) * 2 + (pp->lsoln != 0), k.sm_query_bytes,
-                                              k.sm_entry_bytes, k.sm_mapwords, k.sm_bmapwords, tw_max, n1max};
+                                              k.sm_entry_bytes, k.sm_mapwords, k.sm_bmapwords, tw_max * 64 + teams_cap, n1max};
           auto hit = s->launch_cfg.find(cfg_key);
           if (hit != s->launch_cfg.end()) {
             best_tw = hit->second[0]; best_teams = hit->second[1]; best_team_bytes = hit->second[2]; best_ctas = hit->second[3];
@@ -531,13 +601,13 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
             for (int tw = tw_max; tw >= 32; tw >>= 1) {
               if (tw & 31) continue;             // 96 -> 48: not a whole number of warps
               const int team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * tw * 4 + SATS_K_SCRATCH_BYTES + (size_t)(tw / 32) * k.sm_qmask_bytes);
-              int teams_max = SATS_K_MAXTHREADS / tw;
-              if (const char *e = getenv("SATS_TEAMS")) teams_max = std::max(1, std::min(teams_max, atoi(e)));
+              const int teams_max = std::min(SATS_K_MAXTHREADS / tw, teams_cap);
               for (int teams = teams_max; teams >= 1; teams--) {
                 size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + SATS_K_ZTAB_BYTES + (size_t)teams * team_bytes;
                 if (smem > (size_t)kMaxSmem) continue;
                 int ctas = 0;
                 CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, fn, teams * tw, smem));
+                if (ctas < 1) continue;            // does not fit at all
                 int warps = ctas * teams * tw / 32;
                 if (warps > best_warps) { best_warps = warps; best_teams = teams; best_tw = tw; best_team_bytes = team_bytes; best_ctas = ctas; }
               }
@@ -614,9 +684,10 @@ extern "C" int sats_search_launch(sats_searcher *s, const sats_params *pp, uint3
   }
   return SATS_OK;
 }
+SATS_CATCH_ALL
 
 extern "C" int sats_search_collect(sats_searcher *s, int32_t *scores, int32_t *maps)
-{
+try {
   if (!s || !scores) return sats_fail(SATS_ERR_ARG, "sats_search_collect: null argument");
   if (s->last_lsoln && !maps) return sats_fail(SATS_ERR_ARG, "sats_search_collect: maps buffer required with lsoln");
   CK(cudaSetDevice(s->device));
@@ -642,6 +713,7 @@ extern "C" int sats_search_collect(sats_searcher *s, int32_t *scores, int32_t *m
   }
   return SATS_OK;
 }
+SATS_CATCH_ALL
 
 // ------------------------------------------------------------------------------------------------ top-k
 // One CTA per query slot selects the k best-scoring entries of that query on the device, so only k (position, score)
@@ -741,7 +813,7 @@ sats_topk_kernel(const int32_t *scores, int stride, int count, int k, int32_t *o
 }
 
 extern "C" int sats_search_topk(sats_searcher *s, int k, int32_t *index_out, int32_t *score_out)
-{
+try {
   if (!s || !index_out || !score_out || k < 1) return sats_fail(SATS_ERR_ARG, "sats_search_topk: bad argument");
   if (s->last_q < 1) return sats_fail(SATS_ERR_ARG, "sats_search_topk: no search has been launched");
   CK(cudaSetDevice(s->device));
@@ -800,6 +872,7 @@ extern "C" int sats_search_topk(sats_searcher *s, int k, int32_t *index_out, int
   }
   return SATS_OK;
 }
+SATS_CATCH_ALL
 
 // ---- device-side significance cut ---------------------------------------------------------------------
 // One CTA per query slot.  thr[q][n2] is the smallest raw score whose Gumbel z-score reaches the cut for a structure of
@@ -838,7 +911,7 @@ sats_hits_kernel(const int32_t *scores, int stride, int count, const int32_t *or
 }
 
 extern "C" int sats_search_hits(sats_searcher *s, double z_min, int cap, int32_t *count_out, int32_t *index_out, int32_t *score_out)
-{
+try {
   if (!s || !count_out || !index_out || !score_out || cap < 1) return sats_fail(SATS_ERR_ARG, "sats_search_hits: bad argument");
   if (s->last_q < 1) return sats_fail(SATS_ERR_ARG, "sats_search_hits: no search has been launched");
   if (!(z_min == z_min)) return sats_fail(SATS_ERR_ARG, "sats_search_hits: z_min is NaN");
@@ -885,6 +958,7 @@ extern "C" int sats_search_hits(sats_searcher *s, double z_min, int cap, int32_t
   }
   return SATS_OK;
 }
+SATS_CATCH_ALL
 
 extern "C" int sats_search(sats_searcher *s, const sats_db *queries, int qfirst, int qcount, const sats_params *params,
                            uint32_t query_index_base, int32_t *scores, int32_t *maps)

@@ -15,6 +15,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <new>
 #include <numeric>
 #include <strings.h>
 
@@ -207,6 +209,20 @@ int parse_entries(Cursor &c, const char *what, sats_db *db, int max_order = SATS
   return 0;
 }
 
+// a structure handed over as arrays or read from the packed cache must use the same alphabet the ASCII parser enforces:
+// SSE type 0..3 on the diagonal, letters 0..4 in both nibbles elsewhere (the kernel indexes tables with them)
+int check_codes(const char *what, const char *name, int n, const uint8_t *tri_tab)
+{
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j <= i; j++) {
+      const uint8_t v = tri_tab[(size_t)i * (i + 1) / 2 + j];
+      if (i == j ? v > 3 : ((v >> 4) > 4 || (v & 15) > 4))
+        return sats_fail(SATS_ERR_PARSE, "%s: structure %.8s has invalid %s 0x%02x at (%d, %d)", what, name,
+                         i == j ? "SSE type" : "tableau code", v, i, j);
+    }
+  return 0;
+}
+
 int slurp(const char *path, std::string *out)
 {
   FILE *fp = fopen(path, "rb");
@@ -221,17 +237,18 @@ int slurp(const char *path, std::string *out)
 }  // namespace
 
 extern "C" int sats_db_parse_ascii_ext(const char *text, size_t len, int max_order, sats_db **out)
-{
+try {
   if (!text || !out) return sats_fail(SATS_ERR_ARG, "sats_db_parse_ascii: null argument");
   if (max_order < 1 || max_order > SATS_MAXDIM_EXT) return sats_fail(SATS_ERR_ARG, "max_order %d outside 1..%d", max_order, SATS_MAXDIM_EXT);
-  sats_db *db = new sats_db();
+  std::unique_ptr<sats_db> db(new sats_db());
   db->tri_off.push_back(0);
   Cursor c{text, text + len};
-  int rc = parse_entries(c, "database", db, max_order);
-  if (rc) { delete db; return rc; }
-  *out = db;
+  int rc = parse_entries(c, "database", db.get(), max_order);
+  if (rc) return rc;
+  *out = db.release();
   return SATS_OK;
 }
+SATS_CATCH_ALL
 
 extern "C" int sats_db_parse_ascii(const char *text, size_t len, sats_db **out)
 {
@@ -239,19 +256,20 @@ extern "C" int sats_db_parse_ascii(const char *text, size_t len, sats_db **out)
 }
 
 extern "C" int sats_db_read_ascii_ext(const char *path, int max_order, sats_db **out)
-{
+try {
   if (!path || !out) return sats_fail(SATS_ERR_ARG, "sats_db_read_ascii: null argument");
   std::string text;
   int rc = slurp(path, &text);
   if (rc) return rc;
   return sats_db_parse_ascii_ext(text.data(), text.size(), max_order, out);
 }
+SATS_CATCH_ALL
 
 extern "C" int sats_db_read_ascii(const char *path, sats_db **out) { return sats_db_read_ascii_ext(path, SATS_MAXDIM, out); }
 
 extern "C" int sats_input_parse(const char *text, size_t len, char *dbfile, size_t dbfile_cap, int flags_tf[3],
                                 sats_db **queries)
-{
+try {
   if (!text || !dbfile || !flags_tf || !queries || dbfile_cap < 2) return sats_fail(SATS_ERR_ARG, "sats_input_parse: bad argument");
   Cursor c{text, text + len};
   c.skip_space();
@@ -271,14 +289,15 @@ extern "C" int sats_input_parse(const char *text, size_t len, char *dbfile, size
     f[i] = *c.p++;
   }
   for (int i = 0; i < 3; i++) flags_tf[i] = (f[i] == 'T');
-  sats_db *q = new sats_db();
+  std::unique_ptr<sats_db> q(new sats_db());
   q->tri_off.push_back(0);
-  int rc = parse_entries(c, "query", q);
-  if (rc) { delete q; return rc; }
-  if (q->count() == 0) { delete q; return sats_fail(SATS_ERR_PARSE, "ERROR: no query structures found on stdin"); }
-  *queries = q;
+  int rc = parse_entries(c, "query", q.get());
+  if (rc) return rc;
+  if (q->count() == 0) return sats_fail(SATS_ERR_PARSE, "ERROR: no query structures found on stdin");
+  *queries = q.release();
   return SATS_OK;
 }
+SATS_CATCH_ALL
 
 extern "C" int sats_idlist_parse(const char *text, size_t len, char *ids_out, int max_ids)
 {
@@ -301,16 +320,17 @@ extern "C" int sats_idlist_parse(const char *text, size_t len, char *ids_out, in
 
 extern "C" int sats_db_from_arrays(int count, const int32_t *order, const char *names, const int64_t *off,
                                    const uint8_t *tabs, const float *dmats, sats_db **out)
-{
+try {
   if (count < 0 || !out || (count && (!order || !names || !off || !tabs || !dmats)))
     return sats_fail(SATS_ERR_ARG, "sats_db_from_arrays: bad argument");
-  sats_db *db = new sats_db();
+  std::unique_ptr<sats_db> db(new sats_db());
   db->tri_off.push_back(0);
   std::vector<uint8_t> tt;
   std::vector<float> td;
   for (int e = 0; e < count; e++) {
     int n = order[e];
-    if (n < 1 || n > SATS_MAXDIM_EXT) { delete db; return sats_fail(SATS_ERR_ARG, "entry %d has order %d outside 1..%d", e, n, SATS_MAXDIM_EXT); }
+    if (n < 1 || n > SATS_MAXDIM_EXT) return sats_fail(SATS_ERR_ARG, "entry %d has order %d outside 1..%d", e, n, SATS_MAXDIM_EXT);
+    if (off[e] < 0) return sats_fail(SATS_ERR_ARG, "entry %d has a negative offset", e);
     tt.resize((size_t)n * (n + 1) / 2);
     td.resize(tt.size());
     const uint8_t *t = tabs + off[e];
@@ -322,11 +342,13 @@ extern "C" int sats_db_from_arrays(int count, const int32_t *order, const char *
       }
     char nm[9] = {0};
     memcpy(nm, names + (size_t)e * 9, 8);
+    if (int rc = check_codes("sats_db_from_arrays", nm, n, tt.data())) return rc;
     db->append(nm, n, tt.data(), td.data());
   }
-  *out = db;
+  *out = db.release();
   return SATS_OK;
 }
+SATS_CATCH_ALL
 
 extern "C" void sats_db_free(sats_db *db) { delete db; }
 extern "C" int sats_db_count(const sats_db *db) { return db ? db->count() : 0; }
@@ -361,21 +383,22 @@ extern "C" int sats_db_find(const sats_db *db, const char *name)
 }
 
 extern "C" int sats_db_select(const sats_db *src, const int32_t *index, int count, sats_db **out)
-{
+try {
   if (!src || !out || count < 0 || (count && !index)) return sats_fail(SATS_ERR_ARG, "sats_db_select: bad argument");
-  sats_db *db = new sats_db();
+  std::unique_ptr<sats_db> db(new sats_db());
   db->tri_off.push_back(0);
   for (int k = 0; k < count; k++) {
     int e = index[k];
-    if (e < 0 || e >= src->count()) { delete db; return sats_fail(SATS_ERR_ARG, "sats_db_select: bad index %d", e); }
+    if (e < 0 || e >= src->count()) return sats_fail(SATS_ERR_ARG, "sats_db_select: bad index %d", e);
     db->append(src->name(e), src->order[e], src->tab.data() + src->tri_off[e], src->dmat.data() + src->tri_off[e]);
   }
-  *out = db;
+  *out = db.release();
   return SATS_OK;
 }
+SATS_CATCH_ALL
 
 extern "C" int sats_db_bootstrap(const sats_db *src, int count, uint64_t seed, int sort_by_order, sats_db **out)
-{
+try {
   if (!src || !out || count < 0 || src->count() == 0) return sats_fail(SATS_ERR_ARG, "sats_db_bootstrap: bad argument");
   uint64_t x = seed ? seed : 0x9E3779B97F4A7C15ull;
   std::vector<int32_t> pick((size_t)count);
@@ -388,7 +411,7 @@ extern "C" int sats_db_bootstrap(const sats_db *src, int count, uint64_t seed, i
   std::iota(pos.begin(), pos.end(), 0);
   if (sort_by_order)
     std::stable_sort(pos.begin(), pos.end(), [&](int a, int b) { return src->order[pick[a]] < src->order[pick[b]]; });
-  sats_db *db = new sats_db();
+  std::unique_ptr<sats_db> db(new sats_db());
   db->tri_off.push_back(0);
   char nm[16];
   for (int k = 0; k < count; k++) {
@@ -396,9 +419,10 @@ extern "C" int sats_db_bootstrap(const sats_db *src, int count, uint64_t seed, i
     snprintf(nm, sizeof nm, "s%06d", pos[k] % 1000000);
     db->append(nm, src->order[e], src->tab.data() + src->tri_off[e], src->dmat.data() + src->tri_off[e]);
   }
-  *out = db;
+  *out = db.release();
   return SATS_OK;
 }
+SATS_CATCH_ALL
 
 // ------------------------------------------------------------------------------------------ writers
 // "%6.3f " of a distance without going through printf.  A float times 1000 is exact in double (24 + 10 significant bits),
@@ -429,7 +453,7 @@ static inline void put_distance(std::string &out, float d)
 }
 
 extern "C" int sats_db_write_ascii(const sats_db *db, const char *path)
-{
+try {
   if (!db || !path) return sats_fail(SATS_ERR_ARG, "sats_db_write_ascii: null argument");
   FILE *fp = fopen(path, "w");
   if (!fp) return sats_fail(SATS_ERR_IO, "cannot open %s for writing", path);
@@ -459,6 +483,7 @@ extern "C" int sats_db_write_ascii(const sats_db *db, const char *path)
   if (fclose(fp)) return sats_fail(SATS_ERR_IO, "write error on %s", path);
   return SATS_OK;
 }
+SATS_CATCH_ALL
 
 static const char PACKED_MAGIC[8] = {'S', 'A', 'T', 'S', 'D', 'B', '1', 0};
 
@@ -483,7 +508,7 @@ extern "C" int sats_db_write_packed(const sats_db *db, const char *path)
 }
 
 extern "C" int sats_db_read_packed(const char *path, sats_db **out)
-{
+try {
   if (!path || !out) return sats_fail(SATS_ERR_ARG, "sats_db_read_packed: null argument");
   std::string raw;
   int rc = slurp(path, &raw);
@@ -492,29 +517,36 @@ extern "C" int sats_db_read_packed(const char *path, sats_db **out)
   uint32_t count; uint64_t cells;
   memcpy(&count, raw.data() + 8, 4);
   memcpy(&cells, raw.data() + 16, 8);
+  // every field is bounded by the file size before any arithmetic on it (a corrupt header must not wrap `need`)
+  if ((uint64_t)count > raw.size() / 13 || cells > raw.size() / 5) return sats_fail(SATS_ERR_PARSE, "%s is truncated", path);
   size_t pos = 24;
   size_t need = pos + 13 * (size_t)count + (8 - (13 * (size_t)count) % 8) % 8 + cells + (8 - cells % 8) % 8 + 4 * cells;
   if (raw.size() < need) return sats_fail(SATS_ERR_PARSE, "%s is truncated", path);
-  sats_db *db = new sats_db();
+  std::unique_ptr<sats_db> db(new sats_db());
   db->order.resize(count);
   memcpy(db->order.data(), raw.data() + pos, 4 * (size_t)count); pos += 4 * (size_t)count;
-  db->names.assign(raw.data() + pos, raw.data() + pos + 9 * (size_t)count); pos += 9 * (size_t)count;
-  pos += (8 - (13 * (size_t)count) % 8) % 8;
-  db->tab.assign((const uint8_t *)raw.data() + pos, (const uint8_t *)raw.data() + pos + cells); pos += cells + (8 - cells % 8) % 8;
-  db->dmat.resize(cells);
-  memcpy(db->dmat.data(), raw.data() + pos, 4 * cells);
+  // the orders must account for exactly `cells` triangle cells before anything is copied by them
   db->tri_off.assign(1, 0);
   uint64_t sum = 0;
   for (uint32_t e = 0; e < count; e++) {
     int n = db->order[e];
-    if (n < 1 || n > SATS_MAXDIM_EXT) { delete db; return sats_fail(SATS_ERR_PARSE, "%s: entry %u has order %d", path, e, n); }
+    if (n < 1 || n > SATS_MAXDIM_EXT) return sats_fail(SATS_ERR_PARSE, "%s: entry %u has order %d", path, e, n);
     sum += (uint64_t)n * (n + 1) / 2;
     db->tri_off.push_back((int64_t)sum);
   }
-  if (sum != cells) { delete db; return sats_fail(SATS_ERR_PARSE, "%s: cell count mismatch", path); }
-  *out = db;
+  if (sum != cells) return sats_fail(SATS_ERR_PARSE, "%s: cell count mismatch", path);
+  db->names.assign(raw.data() + pos, raw.data() + pos + 9 * (size_t)count); pos += 9 * (size_t)count;
+  for (uint32_t e = 0; e < count; e++) db->names[(size_t)e * 9 + 8] = 0;
+  pos += (8 - (13 * (size_t)count) % 8) % 8;
+  db->tab.assign((const uint8_t *)raw.data() + pos, (const uint8_t *)raw.data() + pos + cells); pos += cells + (8 - cells % 8) % 8;
+  db->dmat.resize(cells);
+  memcpy(db->dmat.data(), raw.data() + pos, 4 * cells);
+  for (uint32_t e = 0; e < count; e++)
+    if (int crc = check_codes(path, db->name((int)e), db->order[e], db->tab.data() + db->tri_off[e])) return crc;
+  *out = db.release();
   return SATS_OK;
 }
+SATS_CATCH_ALL
 
 // ------------------------------------------------------------------------------------------ statistics
 extern "C" {
@@ -581,7 +613,7 @@ extern "C" size_t sats_format_block(char *buf, size_t cap, const char *query_id,
 
 // ------------------------------------------------------------------------------------------ sharding
 extern "C" int sats_partition(const sats_db *db, int shard_count, int32_t *owner)
-{
+try {
   if (!db || !owner || shard_count < 1) return sats_fail(SATS_ERR_ARG, "sats_partition: bad argument");
   int n = db->count();
   std::vector<int32_t> idx((size_t)n);
@@ -597,6 +629,7 @@ extern "C" int sats_partition(const sats_db *db, int shard_count, int32_t *owner
   }
   return SATS_OK;
 }
+SATS_CATCH_ALL
 
 extern "C" void sats_params_default(sats_params *p)
 {
@@ -620,9 +653,9 @@ struct sats_results {
 };
 
 extern "C" int sats_results_parse(const char *text, size_t len, sats_results **out)
-{
+try {
   if (!text || !out) return sats_fail(SATS_ERR_ARG, "sats_results_parse: null argument");
-  sats_results *r = new sats_results();
+  std::unique_ptr<sats_results> r(new sats_results());
   Cursor c{text, text + len};
   const char *b, *e;
   int lineno = 0;
@@ -656,13 +689,13 @@ extern "C" int sats_results_parse(const char *text, size_t len, sats_results **o
       r->blocks.back().rows.back().pairs.push_back(a);
       r->blocks.back().rows.back().pairs.push_back(bb);
     } else {
-      delete r;
       return sats_fail(SATS_ERR_PARSE, "result line %d not understood: %.60s", lineno, ln.c_str());
     }
   }
-  *out = r;
+  *out = r.release();
   return SATS_OK;
 }
+SATS_CATCH_ALL
 
 extern "C" void sats_results_free(sats_results *r) { delete r; }
 extern "C" int sats_results_blocks(const sats_results *r) { return r ? (int)r->blocks.size() : 0; }

@@ -4,6 +4,8 @@
 
 #include <cstdarg>
 #include <cstdint>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -28,7 +30,13 @@ struct sats_db {
 
 int sats_fail(int status, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
 
-// Cost model used by the partitioner (SURVEY 8e shape a + b*n2, recalibrated on a B200: per-entry kernel time by size
+// C++ exceptions must not cross the C ABI: every entry point that allocates is a function-try-block ending in this
+#define SATS_CATCH_ALL                                                                                         \
+  catch (const std::bad_alloc &) { return sats_fail(SATS_ERR_NOMEM, "out of memory"); }                        \
+  catch (const std::exception &ex) { return sats_fail(SATS_ERR_ARG, "internal error: %s", ex.what()); }
+
+// Cost model used by the partitioner, sats_partition(): greedy longest-processing-time-first over the size-sorted list
+// (SURVEY 8e shape a + b*n2, recalibrated on a B200: per-entry kernel time by size
 // bucket in profiles/r01h_launches.txt is 0.107 us at order ~4 rising linearly to 0.43 us at order ~56, i.e.
 // proportional to 13 + order for the bench query; the shape is what matters for balancing).
 static inline double sats_entry_cost(int order) { return 13.0 + (double)order; }

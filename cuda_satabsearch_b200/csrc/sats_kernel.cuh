@@ -19,11 +19,13 @@
 //     a missing side of a move reads a row of NaN distances, so the loop body is branch-free.
 //   * LSOLN: the best map is kept as (dirty mask, first-change saves) and completed once per chain, never copied
 //     wholesale.
-//   * Metropolis thresholds come from a host-built table of the reference's exact fp32 values
-//     expf((float)delta / T_m) (kernel.cu:1166) or, in DEVICE_FAST mode, from the same fast-math
-//     intrinsics the reference's GPU build uses.
-//   * Uniforms: Philox4x32-10 at static positions (production) or the reference's XORWOW grid streams
-//     consumed in the reference's order (validation).
+//   * No per-move float conversions: every decision the reference takes on a uniform u = unit(x) of 32 random bits x
+//     is a monotone function of x, so the host tabulates it as integer cut-offs with the reference's exact fp32 / fp64
+//     arithmetic -- the SSE pick (int)((u - 1.1e-7) * n1) (kernel.cu:1042) becomes umulhi(x, n1) corrected by one
+//     shared-memory threshold, the Metropolis test expf((float)delta / T_m) > u (kernel.cu:1166) becomes x < cut[m][-delta].
+//     In DEVICE_FAST mode (validation streams only) the test uses the fast-math intrinsics of the reference's GPU build.
+//   * Uniforms: Philox4x32-10 at static positions (production: one block per two moves, one per seeding pass) or the
+//     reference's XORWOW grid streams consumed in the reference's order (validation).
 //   * Restart arg-max: redux.sync inside each warp, then across the team's warps through shared
 //     memory, with the reference's tie-break (kernel.cu:1205-1221).
 #ifndef SATS_KERNEL_CUH
@@ -195,15 +197,29 @@ struct Xorwow {
   uint32_t d, v0, v1, v2, v3, v4;
   __device__ __forceinline__ void load(const uint32_t *p) { d = p[0]; v0 = p[1]; v1 = p[2]; v2 = p[3]; v3 = p[4]; v4 = p[5]; }
   __device__ __forceinline__ void store(uint32_t *p) const { p[0] = d; p[1] = v0; p[2] = v1; p[3] = v2; p[4] = v3; p[5] = v4; }
-  __device__ __forceinline__ float next()
+  __device__ __forceinline__ uint32_t next()      // the 32 bits curand_uniform turns into a float
   {
     uint32_t t = v0 ^ (v0 >> 2);
     v0 = v1; v1 = v2; v2 = v3; v3 = v4;
     v4 = (v4 ^ (v4 << 4)) ^ (t ^ (t << 1));
     d += 362437u;
-    return unit_from_bits(v4 + d);
+    return v4 + d;
   }
 };
+
+// The SSE pick of a move, (int)((unit(x) - 1.1e-7) * n1) in double (kernel.cu:1042), straight from the 32 random bits:
+// unit() is monotone and the pick lies at most one below floor(x * n1 / 2^32) (the shift by 1.1e-7 is less than one step
+// for every n1 <= 111), so one multiply-high and one compare with the host-tabulated exact boundary of that step do it.
+// pick_cut[k] = the smallest x whose pick is >= k (pick_cut[0] = 0): n1 words behind the SSE types in the query header.
+__device__ __forceinline__ int pick_index(uint32_t x, int n1, uint32_t pick_cut)
+{
+  const uint32_t s0 = __umulhi(x, (uint32_t)n1);
+  uint32_t t;
+  asm("ld.shared.b32 %0, [%1];" : "=r"(t) : "r"(pick_cut + s0 * 4u));
+  return (int)s0 - (x < t ? 1 : 0);
+}
+// the production streams' candidate draw: Fibonacci hash of the pick word (stream layout v2)
+__device__ __forceinline__ uint32_t candidate_bits(uint32_t x1) { return x1 * 0x9E3779B9u; }
 
 // ------------------------------------------------------------------------------------------------ scoring
 // tscord (kernel.cu:306-332) as a 128-byte table in shared memory.  A device cell carries its tableau code as
@@ -260,6 +276,7 @@ struct TeamView {
   const uint2 *qcell_g;    // W1 == 4 only: the query's n1 x n1 cells in global memory
   uint32_t qcell;          // n1 x n1 {distance bits, code} (W1 <= 2)
   const uint8_t *qtype;    // n1
+  uint32_t pick_cut;       // n1 words: exact boundaries of the SSE pick (pick_index)
   uint32_t ecell;          // n2 x n2, preceded by "row -1": n2 cells of NaN distance (the missing side of a move)
   uint32_t ztab;           // the zeta table (128-byte aligned)
   const uint32_t *tmask;   // [4][4] type -> 128-bit mask of entry SSEs of that type
@@ -340,27 +357,51 @@ struct Chain {
       if (!bit_test<W1>(dirty, k)) Map<false>::put(v.bmap, k, v.mstride, LiveMap::get(v.smap, k, v.mstride));
   }
 
-  // thinit (kernel.cu:588-648): walk the query, with probability 1/2 match SSE i to the next entry SSE of its type
-  template <class Draw> __device__ __forceinline__ void seed(const TeamView &v, Draw &&draw)
+  __device__ __forceinline__ void seed_clear(const TeamView &v)
   {
 #pragma unroll
     for (int w = 0; w < W1; w++) mq[w] = 0u;
 #pragma unroll
     for (int w = 0; w < W2; w++) md[w] = 0u;
     LiveMap::clear(v.smap, v.n1, v.mstride);
-    int next_j = 0;
-    for (int i = 0; i < v.n1; i++) {
-      float u = draw(i);
-      if (u < 0.5f) {
-        uint32_t cand[W2];
+  }
+  // match query SSE i to the next free entry SSE of its type at or after next_j; false = none left (thinit returns)
+  __device__ __forceinline__ bool seed_pair(const TeamView &v, int i, int &next_j)
+  {
+    uint32_t cand[W2];
 #pragma unroll
-        for (int w = 0; w < W2; w++) cand[w] = lds32(v.qmask + (uint32_t)(i * W2 + w) * 4u);
-        int j = low_at_or_above<W2>(cand, next_j);
-        if (j < 0) break;
-        LiveMap::put(v.smap, i, v.mstride, j);
-        bit_set<W1>(mq, i);
-        bit_set<W2>(md, j);
-        next_j = j + 1;
+    for (int w = 0; w < W2; w++) cand[w] = lds32(v.qmask + (uint32_t)(i * W2 + w) * 4u);
+    const int j = low_at_or_above<W2>(cand, next_j);
+    if (j < 0) return false;
+    LiveMap::put(v.smap, i, v.mstride, j);
+    bit_set<W1>(mq, i);
+    bit_set<W2>(md, j);
+    next_j = j + 1;
+    return true;
+  }
+  // thinit (kernel.cu:588-648): walk the query, with probability 1/2 match SSE i to the next entry SSE of its type.
+  // Validation streams: one draw per query SSE until the entry runs out of SSEs of the wanted type.
+  template <class Attempt> __device__ __forceinline__ void seed(const TeamView &v, Attempt &&attempt)
+  {
+    seed_clear(v);
+    int next_j = 0;
+    for (int i = 0; i < v.n1; i++)
+      if (attempt(i) && !seed_pair(v, i, next_j)) break;
+  }
+  // Production streams: the seeding pass owns one random bit per query SSE (att: the Philox seeding block), so only the
+  // SSEs that do attempt a match are visited.
+  __device__ __forceinline__ void seed_bits(const TeamView &v, const uint32_t (&att)[4])
+  {
+    seed_clear(v);
+    int next_j = 0;
+    bool alive = true;
+#pragma unroll
+    for (int w = 0; w < (W1 < 4 ? W1 : 4); w++) {
+      uint32_t a = att[w] & below(v.n1 - 32 * w);
+      while (a && alive) {
+        const int i = 32 * w + __ffs(a) - 1;
+        a &= a - 1u;
+        alive = seed_pair(v, i, next_j);
       }
     }
   }
@@ -423,9 +464,9 @@ struct Chain {
     return d;
   }
 
-  // One Metropolis move (kernel.cu:1032-1191) on query SSE i = scaled_index(first uniform of the move, n1).  u2/u3 are
-  // callables so that a sequential generator is advanced exactly when the reference would draw (u2 only with >= 2
-  // candidates).
+  // One Metropolis move (kernel.cu:1032-1191) on query SSE i = pick_index(first draw of the move).  u2/u3 are callables
+  // returning 32 random bits, so that a sequential generator is advanced exactly when the reference would draw (u2 only
+  // with >= 2 candidates).
   template <class U2, class U3>
   __device__ __forceinline__ void move(const TeamView &v, int m, const SatsKParams &p, int &best, int &best_tag, int tag,
                                        const int i, U2 &&u2, U3 &&u3)
@@ -463,7 +504,7 @@ struct Chain {
     }
     int to = -1;
     if (ncand == 1) to = select_nth<W2>(cand, 0);
-    else if (ncand > 1) to = select_nth<W2>(cand, scaled_index(u2(), ncand));
+    else if (ncand > 1) to = select_nth<W2>(cand, scaled_index(unit_from_bits(u2()), ncand));
 
     int d = 0;
     if (from >= 0 || to >= 0) d = delta(v, i, from, to);
@@ -474,17 +515,19 @@ struct Chain {
       best_tag = tag;
       if (LSOLN) best_is_live();
     }
-    const float u = u3();
+    // Metropolis: expf((float)d / T_m) > unit(x) (kernel.cu:1166) as x < cut[m][-d], cut tabulated on the host from the
+    // reference's exact fp32 thresholds (d > 0 always passes: the threshold exceeds 1 >= unit(x))
+    const uint32_t x = u3();
     bool accept;
-    if (p.accept_mode == SATS_ACCEPT_DEVICE_FAST) {
-      accept = __expf(__fdividef((float)d, __ldg(p.temps + m))) > u;
+    if (XORWOW && p.accept_mode == SATS_ACCEPT_DEVICE_FAST) {
+      accept = __expf(__fdividef((float)d, __ldg(p.temps + m))) > unit_from_bits(x);
     } else if (d > 0) {
       accept = true;
     } else if (d == 0) {
-      accept = 1.0f > u;
+      accept = x < p.accept_cut0;
     } else {
       int nd = -d;
-      accept = nd <= SATS_K_DCLAMP && __ldg(p.accept_tab + m * (SATS_K_DCLAMP + 1) + nd) > u;
+      accept = nd <= SATS_K_DCLAMP && x < __ldg(p.accept_cut + m * (SATS_K_DCLAMP + 1) + nd);
     }
     if (accept) {
       score = cand_score;
@@ -535,21 +578,11 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
   for (int r = tl; r < chains; r += p.tw) {
     const int tag = XORWOW ? tl : r;
     if (XORWOW) {
-      ch.seed(v, [&](int) { return xw.next(); });
+      ch.seed(v, [&](int) { return xw.next() < p.seed_cut; });
     } else {
-      uint32_t rb[4];
-      int have = -1;
-      ch.seed(v, [&](int i) {
-        if ((i >> 2) != have) {
-          have = i >> 2;
-          philox4x32_10(0x80000000u | (uint32_t)have, (uint32_t)r, entry_orig, query_index, p.seed_lo, p.seed_hi, rb);
-        }
-        uint32_t x = rb[0];
-        if ((i & 3) == 1) x = rb[1];
-        if ((i & 3) == 2) x = rb[2];
-        if ((i & 3) == 3) x = rb[3];
-        return unit_from_bits(x);
-      });
+      uint32_t att[4];
+      philox4x32_10(0x80000000u, (uint32_t)r, entry_orig, query_index, p.seed_lo, p.seed_hi, att);
+      ch.seed_bits(v, att);
     }
     ch.score = ch.full_score(v);
     if (ch.score > best) {
@@ -561,23 +594,22 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
     }
     if (XORWOW) {
       for (int m = 0; m < SATS_K_MOVES; m++)
-        ch.move(v, m, p, best, best_tag, tag, scaled_index(xw.next(), v.n1), [&] { return xw.next(); }, [&] { return xw.next(); });
+        ch.move(v, m, p, best, best_tag, tag, pick_index(xw.next(), v.n1, v.pick_cut), [&] { return xw.next(); }, [&] { return xw.next(); });
     } else {
-      // static draw positions: move m, slot s -> draw 3m + s; four moves consume three Philox blocks
+      // static draw positions: Philox block g feeds moves 2g (words 0, 1) and 2g + 1 (words 2, 3); per move the first word
+      // picks the SSE (and, hashed, the candidate), the second is the Metropolis draw
       for (int g = 0; g < SATS_K_MOVES / 4; g++) {
-        uint32_t a[4], b[4], c[4];
-        philox4x32_10(3u * g + 0u, (uint32_t)r, entry_orig, query_index, p.seed_lo, p.seed_hi, a);
-        philox4x32_10(3u * g + 1u, (uint32_t)r, entry_orig, query_index, p.seed_lo, p.seed_hi, b);
-        philox4x32_10(3u * g + 2u, (uint32_t)r, entry_orig, query_index, p.seed_lo, p.seed_hi, c);
+        uint32_t a[4], b[4];
+        philox4x32_10(2u * g + 0u, (uint32_t)r, entry_orig, query_index, p.seed_lo, p.seed_hi, a);
+        philox4x32_10(2u * g + 1u, (uint32_t)r, entry_orig, query_index, p.seed_lo, p.seed_hi, b);
         const int m = 4 * g;
-        // the SSE picks depend on the uniforms only, not on the chains' state: four independent conversion chains
-        // (XU and FP64 pipes) issued together, off the critical path of the moves
-        const int i0 = scaled_index(unit_from_bits(a[0]), v.n1), i1 = scaled_index(unit_from_bits(a[3]), v.n1);
-        const int i2 = scaled_index(unit_from_bits(b[2]), v.n1), i3 = scaled_index(unit_from_bits(c[1]), v.n1);
-        ch.move(v, m + 0, p, best, best_tag, tag, i0, [&] { return unit_from_bits(a[1]); }, [&] { return unit_from_bits(a[2]); });
-        ch.move(v, m + 1, p, best, best_tag, tag, i1, [&] { return unit_from_bits(b[0]); }, [&] { return unit_from_bits(b[1]); });
-        ch.move(v, m + 2, p, best, best_tag, tag, i2, [&] { return unit_from_bits(b[3]); }, [&] { return unit_from_bits(c[0]); });
-        ch.move(v, m + 3, p, best, best_tag, tag, i3, [&] { return unit_from_bits(c[2]); }, [&] { return unit_from_bits(c[3]); });
+        // the SSE picks depend on the draws only, not on the chains' state: issued together, off the moves' critical path
+        const int i0 = pick_index(a[0], v.n1, v.pick_cut), i1 = pick_index(a[2], v.n1, v.pick_cut);
+        const int i2 = pick_index(b[0], v.n1, v.pick_cut), i3 = pick_index(b[2], v.n1, v.pick_cut);
+        ch.move(v, m + 0, p, best, best_tag, tag, i0, [&] { return candidate_bits(a[0]); }, [&] { return a[1]; });
+        ch.move(v, m + 1, p, best, best_tag, tag, i1, [&] { return candidate_bits(a[2]); }, [&] { return a[3]; });
+        ch.move(v, m + 2, p, best, best_tag, tag, i2, [&] { return candidate_bits(b[0]); }, [&] { return b[1]; });
+        ch.move(v, m + 3, p, best, best_tag, tag, i3, [&] { return candidate_bits(b[2]); }, [&] { return b[3]; });
       }
     }
     if (LSOLN) ch.finish_best_map(v);
@@ -640,6 +672,7 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
   TeamView v;
   v.mstride = (uint32_t)p.tw * 4u;
   v.qtype = sq + 16;
+  v.pick_cut = smem_u32(sq + SATS_K_QUERY_PICK);
   // Queries of more than 64 SSEs (W1 == 4) keep their n1 x n1 cells in global memory (read through L1 with ld.global.nc):
   // an 82 KB query copy per CTA would leave room for one CTA per SM.  Only header + SSE types are staged then.
   v.qcell_g = reinterpret_cast<const uint2 *>(p.qblobs + p.qblob_off[qi] + SATS_K_QUERY_HDR);
@@ -698,7 +731,7 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
       phase ^= 1u;
       v.n2 = eh[0];
       v.ecell = ecell0 + 8u * (uint32_t)v.n2;
-      anneal_entry<W1, W2, LORDER, false, LSOLN>(p, v, team, tl, red + 4 * par, (uint32_t)eh[1], (uint32_t)qh[1], xw, qi, p.item_first + idx,
+      anneal_entry<W1, W2, LORDER, false, LSOLN>(p, v, team, tl, red + 4 * par, (uint32_t)eh[1], p.q_index_base + (uint32_t)qh[1], xw, qi, p.item_first + idx,
                                                  [&] { if (tl == 0) claim_next(par ^ 1); },
                                                  [&] { if (tl == 0) fetch(claim[par ^ 1]); });
     }
@@ -729,7 +762,7 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
       const int32_t *eh = reinterpret_cast<const int32_t *>(se);
       v.n2 = eh[0];
       v.ecell = ecell0 + 8u * (uint32_t)v.n2;
-      anneal_entry<W1, W2, LORDER, true, LSOLN>(p, v, 0, tl, red, (uint32_t)eh[1], (uint32_t)qh[1], xw, qi, e, [] {}, [] {});
+      anneal_entry<W1, W2, LORDER, true, LSOLN>(p, v, 0, tl, red, (uint32_t)eh[1], p.q_index_base + (uint32_t)qh[1], xw, qi, e, [] {}, [] {});
       __syncthreads();       // the entry buffer and the arg-max scratch are reused by the next entry
     }
     xw.store(st);

@@ -9,7 +9,8 @@
 #define SATS_K_DCLAMP 229          // expf(-d/T) <= 2^-33 (smallest uniform) for every d >= 229 and T <= 10
 #define SATS_K_NEG_INIT (-99999)
 #define SATS_K_ENTRY_HDR 80        // 16 B header + 4 types x 4 words of type masks; then one row of NaN cells, then the matrix
-#define SATS_K_QUERY_HDR 128       // 16 B header + 112 B of SSE types
+#define SATS_K_QUERY_PICK 128      // query header: 16 B (n1, position in the batch) + 112 B of SSE types, then ...
+#define SATS_K_QUERY_HDR 576       // ... 112 words of SSE-pick boundaries (pick_index() in sats_kernel.cuh); then the cells
 #define SATS_K_BAR_BYTES 128       // shared-memory header: 1 + teams mbarriers (teams <= 12)
 #define SATS_K_ZTAB_BYTES 256      // shared-memory room for the 128-byte zeta table at a 128-byte aligned address
 #define SATS_K_SCRATCH_BYTES 80     // per team: two alternating arg-max buffers (4 x 8 B each) and two claim slots
@@ -46,7 +47,10 @@ struct SatsKParams {
   // search parameters
   int restarts, lsoln, accept_mode;
   uint32_t seed_lo, seed_hi;
-  const float *accept_tab;         // [SATS_K_MOVES][SATS_K_DCLAMP + 1]
+  const uint32_t *accept_cut;      // [SATS_K_MOVES][SATS_K_DCLAMP + 1]: accept a move of score change -d at step m iff draw < cut
+  uint32_t accept_cut0;            // the cut-off for d == 0 (unit(x) < 1.0f), the same at every step
+  uint32_t seed_cut;               // validation streams: the seeding pass attempts a match iff draw < seed_cut (unit(x) < 0.5)
+  uint32_t q_index_base;           // Philox query index = q_index_base + the query's position in the batch (header word 1)
   const float *temps;              // [SATS_K_MOVES]: T_m = 10 * 0.95^m accumulated in fp32 like kernel.cu:1189
   // outputs, indexed [query slot][sorted entry index]
   int32_t *out_scores;

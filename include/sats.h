@@ -143,7 +143,9 @@ double sats_roc_auc(const double *score, const uint8_t *positive, int n);
 
 typedef enum sats_rng_mode {
   /* Production: Philox4x32-10 keyed by seed, counter = (draw block, restart, original entry index,
-   * query index); exactly `restarts` chains per entry, independent of launch geometry.           */
+   * query index); exactly `restarts` chains per entry, independent of launch geometry.  One block
+   * per two moves (SSE pick + candidate pick from one word, Metropolis draw from the next) and one
+   * block of seeding bits per chain: DESIGN.md "stream layout v2".                                */
   SATS_RNG_PHILOX = 0,
   /* Validation: the reference GPU run's 128 x 128 XORWOW streams (curand_init(seed, tid, 0)), block b
    * walking entries b, b+128, ... of the pool in file order, restarts rounded up to a multiple of
@@ -156,7 +158,8 @@ typedef enum sats_accept_mode {
    * fp32 values the reference's `-c` path compares against (kernel.cu:1166).                     */
   SATS_ACCEPT_HOST_TABLE = 0,
   /* __expf(__fdividef(delta, T)) evaluated on the device: what the reference's GPU build does under
-   * its --use_fast_math (Makefile:51).  For same-box parity with the reference GPU binary.       */
+   * its --use_fast_math (Makefile:51).  For same-box parity with the reference GPU binary, hence
+   * only with SATS_RNG_XORWOW_GRID (SATS_ERR_ARG otherwise).                                      */
   SATS_ACCEPT_DEVICE_FAST = 1
 } sats_accept_mode;
 
@@ -187,17 +190,23 @@ void sats_params_default(sats_params *p);
  * of {fp32 distance, tableau code}), plus streams, the XORWOW state grid and result buffers.     */
 typedef struct sats_searcher sats_searcher;
 
-/* shard_count <= 1: whole db.  Otherwise this searcher holds shard `shard_rank` of a cost-weighted
- * partition of the size-sorted db into shard_count parts (Philox mode), see sats_partition().
- * In XORWOW_GRID mode a shard instead owns the reference blocks b with b % shard_count == rank.  */
+/* shard_count <= 1: whole db.  Otherwise this searcher holds part `shard_rank` of sats_partition(db,
+ * shard_count): production (Philox) mode only -- chains are keyed by original entry index, so any split
+ * of the entries gives the unsharded results.  XORWOW_GRID searches on such a searcher fail with
+ * SATS_ERR_ARG: the validation streams belong to reference BLOCKS walking the whole pool, so a multi-GPU
+ * validation run keeps the database replicated (shard_count 1 on every GPU) and splits the blocks with
+ * sats_params.grid_rank / grid_count (block b runs where b % grid_count == grid_rank; merge the scores,
+ * and take block b's final states from its owner).                                                    */
 int sats_searcher_create(const sats_db *db, int device, int shard_rank, int shard_count,
                          sats_searcher **out);
 void sats_searcher_free(sats_searcher *s);
 int sats_searcher_entry_count(const sats_searcher *s);      /* entries resident on this GPU        */
 int sats_searcher_device(const sats_searcher *s);
 
-/* Cost-weighted partition: owner[e] in [0, shard_count) for every db entry, balancing
- * sum of cost(order) = a + b*min(order, 40) over shards of the size-sorted list.                 */
+/* Cost-weighted partition: owner[e] in [0, shard_count) for every db entry.  Greedy
+ * longest-processing-time-first: the entries in decreasing order of size are dealt one by one to the
+ * shard with the least accumulated cost, cost(order) = 13 + order (the measured per-entry kernel time
+ * on a B200 is proportional to it, csrc/sats_internal.h).  Parts are interleaved, not contiguous.    */
 int sats_partition(const sats_db *db, int shard_count, int32_t *owner);
 
 /* One-shot search: upload queries[qfirst .. qfirst+qcount), run, copy back.
@@ -239,6 +248,18 @@ int sats_searcher_get_xorwow(sats_searcher *s, uint32_t *states6);
 int sats_searcher_reset_xorwow(sats_searcher *s, uint64_t seed);
 
 int sats_device_count(void);
+
+/* ---- validation aids: the integer cut-offs the kernel compares raw 32-bit draws with ----------------------------------
+ * Every decision the reference takes on a uniform u = curand_uniform-style unit(x) of 32 random bits x is monotone in x,
+ * so the library tabulates it once with the reference's own fp32 / fp64 expressions and the kernel never converts a draw
+ * (csrc/sats_device.cu).  Exported so that tests can check the tables against an independent restatement.
+ *   sats_pick_boundaries  cut[k], k < n: smallest x with (int)((unit(x) - 1.1e-7) * n) >= k   (kernel.cu:67, :1042)
+ *   sats_accept_cutoffs   cut[100][230]: a move of score change -d at step m passes iff x < cut[m][d], i.e. iff
+ *                         expf((float)(-d) / T_m) > unit(x) (kernel.cu:1166); temps[100] (may be NULL) = T_m in fp32
+ *   sats_seed_cutoff      smallest x with unit(x) >= 0.5 (INIT_MATCHPROB, saparams.h:43)                           */
+int sats_pick_boundaries(int n, uint32_t *cut);
+int sats_accept_cutoffs(uint32_t *cut, float *temps);
+uint32_t sats_seed_cutoff(void);
 
 #ifdef __cplusplus
 }

@@ -30,8 +30,17 @@
  *         entries b, b+B, ...; thread t runs restarts t, t+T, ... (restart count rounded up to a multiple
  *         of T); per-thread running maximum; block arg-max with lowest-t tie-break; states persist.
  *   (iii) SATS_ORNG_PHILOX   the product's production mode: chain (query, entry id, restart) draws from
- *         Philox4x32-10 at *static* positions (query SSE i of the seeding pass -> draw i; move m, slot s -> draw 3m+s),
- *         so every chain is independent of every other and of the launch geometry.
+ *         Philox4x32-10 at *static* positions, so every chain is independent of every other and of the
+ *         launch geometry.  Stream layout "v2" (counter word 0 selects the block):
+ *           seeding pass  block 0x80000000: one random BIT per query SSE (bit i&31 of word i>>5); the draw is
+ *                         0.25f when the bit is set and 0.75f when it is clear (thinit only compares it with 0.5)
+ *           move m        block m>>1, words 2(m&1) and 2(m&1)+1:
+ *                         u1 (SSE pick)        = unit(word a)
+ *                         u2 (candidate pick)  = unit(word a * 0x9E3779B9)   -- drawn only with >= 2 candidates, like
+ *                                                the reference; the pick uses the leading bits of word a, the Fibonacci
+ *                                                hash spreads the remaining ones
+ *                         u3 (Metropolis test) = unit(word b)
+ *         i.e. one Philox block per two moves and one per seeding pass.
  */
 #include <math.h>
 #include <stdint.h>
@@ -97,6 +106,7 @@ static float u32_to_unit(uint32_t x)
 }
 
 #define DOMAIN_SEED 0x80000000u  /* Philox counter word 0: top bit separates the seeding pass from the moves */
+#define PHILOX_U2_HASH 0x9E3779B9u /* 2^32 / golden ratio: Fibonacci hashing of the pick word into the candidate draw */
 
 static float draw(usrc_t *r, uint32_t domain, uint32_t position)
 {
@@ -106,13 +116,20 @@ static float draw(usrc_t *r, uint32_t domain, uint32_t position)
   case SATS_ORNG_XORWOW:
     return u32_to_unit(xorwow_next(r->xw));
   default: {
-    uint32_t block = domain | (position >> 2);
+    /* `position` is the draw's logical position: query SSE i in the seeding pass, 3*move + slot in the moves */
+    uint32_t block = domain == DOMAIN_SEED ? DOMAIN_SEED : (position / 3u) >> 1;
     if (block != r->cached_block) {
       uint32_t ctr[4] = { block, r->chain[0], r->chain[1], r->chain[2] };
       sats_oracle_philox4x32_10(ctr, r->key, r->cache);
       r->cached_block = block;
     }
-    return u32_to_unit(r->cache[position & 3u]);
+    if (domain == DOMAIN_SEED)
+      return ((r->cache[(position >> 5) & 3u] >> (position & 31u)) & 1u) ? 0.25f : 0.75f;
+    uint32_t move = position / 3u, slot = position % 3u;
+    uint32_t a = r->cache[2u * (move & 1u)], b = r->cache[2u * (move & 1u) + 1u];
+    if (slot == 0u) return u32_to_unit(a);
+    if (slot == 1u) return u32_to_unit(a * PHILOX_U2_HASH);
+    return u32_to_unit(b);
   }
   }
 }
@@ -467,6 +484,15 @@ float sats_oracle_accept_threshold(int mv, int d)
   float temp = ORACLE_T0;
   for (int k = 0; k < mv; k++) temp *= ORACLE_COOL;
   return expf((float)d / temp);
+}
+
+/* What the product's integer thresholds must reproduce, as functions of the raw 32 random bits:
+ * the SSE / candidate pick (kernel.cu:1042, :710) and the Metropolis test (kernel.cu:1166) on unit(x). */
+int sats_oracle_pick_from_bits(uint32_t x, int n) { return scaled_index(u32_to_unit(x), n); }
+int sats_oracle_seed_attempt_from_bits(uint32_t x) { return (double)u32_to_unit(x) < ORACLE_SEEDPROB; }
+int sats_oracle_accept_from_bits(int mv, int d, uint32_t x)
+{
+  return sats_oracle_accept_threshold(mv, d) > u32_to_unit(x);
 }
 
 /* ------------------------------------------------------------------ Gumbel statistics (gumbelstats.c:50-94) */

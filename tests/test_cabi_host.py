@@ -235,3 +235,55 @@ def test_fast_distance_parse_equals_strtof_for_every_canonical_value():
     vb = np.array([b.get(i)[1][0, 0] for i in range(100000)], np.float32)
     assert np.array_equal(va.view(np.uint32), vb.view(np.uint32))
     assert abs(float(va[-1]) - 99.999) < 1e-5 and (np.diff(va) > 0).all()
+
+
+def test_constructors_reject_codes_outside_the_alphabet(tmp_path):
+    """Only the ASCII parser used to validate codes; arrays and the packed cache now apply the same alphabet (the kernel
+    indexes shared-memory tables with the SSE type and the letters)."""
+    tab = np.array([[0, 0x11], [0x11, 1]], np.uint8)
+    dm = np.zeros((2, 2), np.float32)
+    S.Database.from_structures(["ok"], [tab], [dm])
+    for bad in ([[4, 0x11], [0x11, 1]], [[0, 0x51], [0x51, 1]], [[0, 0x15], [0x15, 1]], [[0, 0xff], [0xff, 3]]):
+        with pytest.raises(S.SatsError, match="invalid"):
+            S.Database.from_structures(["bad"], [np.array(bad, np.uint8)], [dm])
+    good = tmp_path / "good.satsdb"
+    S.Database.from_structures(["ok"], [tab], [dm]).write_packed(good)
+    raw = bytearray(good.read_bytes())
+    assert len(S.Database.read_packed(good)) == 1
+    tab_at = 24 + 16                       # header, then order[1] + name[9] padded to 16
+    raw[tab_at] = 9                        # SSE type 9 on the diagonal
+    bad = tmp_path / "bad.satsdb"
+    bad.write_bytes(bytes(raw))
+    with pytest.raises(S.SatsError, match="invalid SSE type"):
+        S.Database.read_packed(bad)
+
+
+def test_packed_reader_survives_corrupt_headers(tmp_path):
+    src = GOLDEN / "test1.satsdb"
+    raw = bytearray(src.read_bytes())
+    for cells in (0x3333333333333334, 0xffffffffffffffff, 1 << 40):        # wrap-around and absurd sizes
+        r = bytearray(raw)
+        r[16:24] = int(cells).to_bytes(8, "little")
+        p = tmp_path / "c.satsdb"
+        p.write_bytes(bytes(r))
+        with pytest.raises(S.SatsError, match="truncated|mismatch"):
+            S.Database.read_packed(p)
+    r = bytearray(raw)
+    r[8:12] = (0xffffffff).to_bytes(4, "little")
+    (tmp_path / "n.satsdb").write_bytes(bytes(r))
+    with pytest.raises(S.SatsError, match="truncated"):
+        S.Database.read_packed(tmp_path / "n.satsdb")
+    r = bytearray(raw)
+    r[24:28] = (5000).to_bytes(4, "little")                                   # an order the cell count cannot hold
+    (tmp_path / "o.satsdb").write_bytes(bytes(r))
+    with pytest.raises(S.SatsError, match="order|mismatch"):
+        S.Database.read_packed(tmp_path / "o.satsdb")
+
+
+def test_shim_checks_caller_buffers():
+    from cuda_satabsearch_b200 import _out_array
+    ok = np.zeros((2, 5), np.int32)
+    assert _out_array(ok, (2, 5), "scores") is ok
+    for bad in (np.zeros((2, 5), np.float64), np.zeros((2, 4), np.int32), np.zeros((5, 2), np.int32).T, np.zeros((2, 10), np.int32)[:, ::2]):
+        with pytest.raises(S.SatsError, match="scores must be"):
+            _out_array(bad, (2, 5), "scores")

@@ -37,6 +37,43 @@ def test_cli_stdout_equals_reference_gpu_binary(tmp_path, fixtures, qnames, lord
     assert ours.stdout == ref.stdout
 
 
+@pytest.mark.skipif(not REF_BIN.exists(), reason="reference binary not built")
+def test_cli_equals_reference_gpu_binary_with_a_large_pool(tmp_path, fixtures):
+    """The reference switches kernels for structures of order 97..111 (sa_tabsearch_gpu_noshared, cudaSaTabsearch.cu:1223) and
+    carries the one state grid from the small-pool launches into the large-pool ones (:1051, :1232).  Three planted large
+    structures (orders 101, 101, 99): names, raw scores and SSE maps must equal the reference's, on one GPU and on two.
+    One query only: with several, the reference's large-pool loop searches with the LAST small-pool query's order and SSE
+    types (stale qn / qssetypes, :1196-1207), a defect this build does not reproduce."""
+    from _refio import Structure
+    src = fixtures["queries_by_name"]["d1twfa_"]           # order 101
+    clamp = np.minimum(src.dmat, np.float32(99.999))       # distances >= 100 A break the 7-column format (SURVEY A.8)
+    ents = list(fixtures["small586"][:140])
+    ents.insert(17, Structure("bigone_", src.tab.copy(), clamp.copy()))
+    rev = np.arange(101)[::-1]
+    ents.insert(90, Structure("bigtwo_", src.tab[np.ix_(rev, rev)].copy(), clamp[np.ix_(rev, rev)].copy()))
+    ents.append(Structure("bigtre_", src.tab[:99, :99].copy(), clamp[:99, :99].copy()))
+    qs = [fixtures["queries_by_name"]["D2PHLB1"]]
+    write_ascii_db(tmp_path / "db.ascii", ents)
+    write_query_input(tmp_path / "q.input", "db.ascii", True, True, qs)
+    ref = run([REF_BIN, "-r", 128], tmp_path / "q.input", tmp_path)
+    assert ref.returncode == 0, ref.stderr.decode()[-1500:]
+    assert ref.stdout.count(b"# QUERY ID") == 2                      # one query x two pools
+    # the reference's large-pool rows carry a double space before the p-value (cudaSaTabsearch.cu:1261): compare names, raw
+    # scores and SSE maps, which is what the kernels produce
+    def rows(text):
+        out = []
+        for ln in text.decode().split("\n"):
+            if not ln or ln.startswith("#"):
+                continue
+            t = ln.split()
+            out.append((t[0], int(t[1])) if len(t) == 5 else ("map", int(t[0]), int(t[1])))
+        return out
+    for g in (1, 2):
+        ours = run([CLI, "-r", 128, "-R", "xorwow", "-A", "fast", "-g", g], tmp_path / "q.input", tmp_path)
+        assert ours.returncode == 0, ours.stderr.decode()[-1500:]
+        assert rows(ours.stdout) == rows(ref.stdout), g
+
+
 def test_cli_production_mode_equals_oracle_rendering(tmp_path, fixtures, oracle):
     """Philox mode, db with both pools (threshold 96 -> plant two large structures), two queries, LSOLN=T."""
     ents = list(fixtures["small586"][:150])

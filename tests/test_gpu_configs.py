@@ -110,6 +110,25 @@ def test_config5_full_size_properties(base, fixtures):
     assert np.all(a[0] <= mn * (mn - 1))
 
 
+@pytest.mark.parametrize("lsoln", [False, True])
+def test_config5_headline_db_against_oracle(base, fixtures, oracle, lsoln):
+    """configs[4], the workload the bench line is quoted on: D2PHLB1 vs the 100 000-structure db, 128 restarts.  A
+    size-stratified sample of 320 entries (every 312th of the size-sorted db, plus the largest ones) is bit-compared with
+    the oracle -- scores, and SSE maps in the LSOLN = T case -- out of the full-size run."""
+    db = base.bootstrap(100000, 20240502, True)
+    q = fixtures["queries_by_name"]["D2PHLB1"]
+    sr = S.Searcher(db, 0)
+    p = S.default_params(lorder=1, lsoln=int(lsoln), restarts=128, seed=1234)
+    sc, mp = sr.search(as_db([q]), p)
+    sr.close()
+    pick = np.unique(np.concatenate([np.arange(0, 100000, 312), np.arange(99990, 100000)])).astype(np.int32)
+    assert len(pick) >= 320
+    ws, wm = oracle.search_philox(q, structures_of(db, pick), entry_ids=pick, lorder=True, lsoln=lsoln, restarts=128, seed=1234)
+    assert np.array_equal(sc[0, pick], ws)
+    if lsoln:
+        assert np.array_equal(mp[0, pick, :q.n], wm[:, :q.n])
+
+
 def test_production_mode_agrees_statistically_with_reference(base, fixtures, golden, oracle):
     """North star, part 2: Philox streams differ from drand48, so per-entry scores differ run to run, but the ranking
     quality must be the same.  Truth = the reference's own converged run (its captured 2013 job, 4096 restarts).

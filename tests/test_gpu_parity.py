@@ -140,6 +140,59 @@ def test_xorwow_pools_follow_reference_launch_order(fixtures, small586, oracle):
     sr.close()
 
 
+@pytest.mark.parametrize("ngrid", [2, 3])
+def test_xorwow_block_sharding_over_replicated_db(fixtures, small586, oracle, ngrid):
+    """SURVEY 8(e), validation mode on several GPUs: the db is replicated, searcher g runs the reference blocks b with
+    b % N == g (cudaSaTabsearch_kernel.cu:932 `dbi = blockIdx.x; dbi += gridDim.x`).  Merged scores and maps, and the final
+    state grid taken block-wise from its owner, must equal the unsharded oracle run -- over two queries and both pools, so
+    that the streams' carry-over (devStates shared by the launches, cudaSaTabsearch.cu:1051, :1232) is exercised too."""
+    ents = small586[:260]
+    qs = [fixtures["queries_by_name"][n] for n in ("D1UBIA_", "D2PHLB1")]
+    small, large = split_pools(ents, 32)
+    assert len(large) > 5
+    states = oracle.xorwow_states(128 * 128, 1234)
+    names = [s.name for s in ents]
+    want_s = np.zeros((2, len(ents)), np.int32)
+    want_m = np.full((2, len(ents), S.MAP_STRIDE), -1, np.int32)
+    for pool in (small, large):
+        ids = [names.index(s.name) for s in pool]
+        for k, q in enumerate(qs):
+            sc, mp = oracle.search_xorwow_grid(q, pool, states, lorder=True, lsoln=True, restarts=128)
+            want_s[k, ids] = sc
+            want_m[k, ids, :q.n] = mp[:, :q.n]
+    db = to_db(ents)
+    got_s = np.full((2, len(ents)), -7, np.int32)
+    got_m = np.full((2, len(ents), S.MAP_STRIDE), -1, np.int32)
+    searchers = [S.Searcher(db, 0) for _ in range(ngrid)]
+    for pool_id in (S.POOL_SMALL, S.POOL_LARGE):
+        for g, sr in enumerate(searchers):
+            p = S.default_params(lorder=1, lsoln=1, restarts=128, rng_mode=S.RNG_XORWOW_GRID, pool=pool_id, pool_threshold=32,
+                                 grid_rank=g, grid_count=ngrid)
+            sr.search(to_db(qs), p, scores=got_s, maps=got_m)
+    assert np.array_equal(got_s, want_s)
+    for k, q in enumerate(qs):
+        assert np.array_equal(got_m[k, :, :q.n], want_m[k, :, :q.n])
+    merged = np.zeros_like(states)
+    for g, sr in enumerate(searchers):
+        st = sr.xorwow_states().reshape(128, 128, 6)
+        merged.reshape(128, 128, 6)[g::ngrid] = st[g::ngrid]
+        sr.close()
+    assert np.array_equal(merged, states)
+
+
+def test_xorwow_refuses_an_entry_sharded_searcher(small586, fixtures):
+    """A searcher holding one part of the cost-weighted partition cannot reproduce the reference blocks' walk over the
+    whole pool: validation mode must say so instead of returning non-reference scores."""
+    sr = S.Searcher(to_db(small586[:64]), 0, 1, 2)
+    q = to_db([fixtures["queries_by_name"]["D1UBIA_"]])
+    with pytest.raises(S.SatsError, match="grid_rank"):
+        sr.search(q, S.default_params(rng_mode=S.RNG_XORWOW_GRID))
+    with pytest.raises(S.SatsError, match="XORWOW_GRID"):
+        sr.search(q, S.default_params(accept_mode=S.ACCEPT_DEVICE_FAST))      # fast-math acceptance is a validation aid
+    sr.search(q, S.default_params())                                            # production mode is what shards are for
+    sr.close()
+
+
 REF_BIN = REPO / "oracle" / "_ref" / "cudaSaTabsearch_ref"
 
 

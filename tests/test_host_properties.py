@@ -90,3 +90,57 @@ def test_ascii_writer_formats_distances_like_printf(tmp_path):
             want = "".join("%6.3f " % (0.0 if np.isnan(dm[i, j]) else float(dm[i, j])) for j in range(i + 1))
             assert lines[pos + i] == want, (name, i)
         pos += n
+
+
+# ---- the kernel's integer cut-offs against the oracle's float / double formulas (reference kernel.cu:1042, :1166, :624)
+def _around(cuts, rng, extra=2000):
+    pts = set()
+    for c in np.asarray(cuts, np.uint64).ravel().tolist():
+        for d in (-2, -1, 0, 1, 2):
+            if 0 <= c + d <= 0xffffffff:
+                pts.add(int(c + d))
+    pts |= {0, 1, 0xffffffff, 0xfffffffe, 0x7fffffc0, 0x7fffffbf, 0x80000000}
+    pts |= set(int(v) for v in rng.integers(0, 2**32, extra, dtype=np.uint64))
+    return sorted(pts)
+
+
+def test_sse_pick_boundaries_reproduce_the_reference_pick(oracle):
+    """pick_index() in the kernel = umulhi(x, n) - (x < cut[umulhi(x, n)]); it must equal the reference's
+    (int)((unit(x) - 1.1e-7) * n) for every x: checked at and around every boundary and on random draws, for every n."""
+    import cuda_satabsearch_b200 as S
+    f = oracle.lib.sats_oracle_pick_from_bits
+    rng = np.random.default_rng(11)
+    for n in range(1, 112):
+        cut = S.pick_boundaries(n)
+        assert cut[0] == 0 and (np.diff(cut.astype(np.int64)) > 0).all()
+        for x in _around(cut, rng, 300 if n % 10 else 3000):
+            s0 = (x * n) >> 32
+            assert s0 - (1 if x < int(cut[s0]) else 0) == f(x, n), (n, x)
+
+
+def test_accept_cutoffs_reproduce_the_reference_metropolis_test(oracle):
+    import cuda_satabsearch_b200 as S
+    cut, temps = S.accept_cutoffs()
+    f = oracle.lib.sats_oracle_accept_from_bits
+    thr = oracle.lib.sats_oracle_accept_threshold
+    rng = np.random.default_rng(12)
+    t = np.float32(10.0)
+    for m in range(100):
+        assert temps[m] == t
+        t = np.float32(t * np.float32(0.95))
+    assert (cut[:, 0] == cut[0, 0]).all() and cut[0, 0] == 0xffffff80          # d == 0: unit(x) < 1.0f
+    assert (np.diff(cut.astype(np.int64), axis=1) <= 0).all()                    # a larger loss is never easier to accept
+    for m in (0, 1, 17, 50, 98, 99):
+        for nd in list(range(0, 40)) + [77, 150, 229]:
+            c = int(cut[m, nd])
+            for x in {max(c - 1, 0), c, min(c + 1, 0xffffffff), 0, 0xffffffff, int(rng.integers(0, 2**32))}:
+                assert (x < c) == bool(f(m, -nd, x)), (m, nd, x, c, thr(m, -nd))
+    # beyond the table: expf(-d / T) <= 2^-33 for d >= 229 even at T = 10, so such moves never pass
+    assert not f(0, -230, 0) and int(cut[0, 229]) == 0
+
+
+def test_seed_cutoff(oracle):
+    import cuda_satabsearch_b200 as S
+    c = S.seed_cutoff()
+    f = oracle.lib.sats_oracle_seed_attempt_from_bits
+    assert f(c - 1) == 1 and f(c) == 0 and f(0) == 1 and f(0xffffffff) == 0
