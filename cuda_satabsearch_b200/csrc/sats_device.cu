@@ -500,7 +500,10 @@ try {
   k.blobs = s->d_blobs; k.blob_off = s->d_blob_off; k.blob_bytes = s->d_blob_bytes;
   k.qblobs = s->d_qblobs; k.qblob_off = s->d_qoff; k.qblob_bytes = s->d_qbytes;
   k.restarts = pp->restarts; k.lsoln = pp->lsoln; k.accept_mode = pp->accept_mode;
-  k.seed_lo = (uint32_t)seed; k.seed_hi = (uint32_t)(seed >> 32);
+  for (uint32_t r = 0; r < 10; r++) {
+    k.rk[2 * r] = (uint32_t)seed + r * 0x9E3779B9u;
+    k.rk[2 * r + 1] = (uint32_t)(seed >> 32) + r * 0xBB67AE85u;
+  }
   k.accept_cut = s->d_accept;
   k.accept_cut0 = s->accept_cut0;
   k.seed_cut = s->seed_cut;

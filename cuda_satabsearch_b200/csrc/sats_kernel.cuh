@@ -180,15 +180,23 @@ __device__ __forceinline__ int scaled_index(float u, int n)
   return (int)(((double)u - 1.1e-7) * (double)n);
 }
 
+// Philox4x32-10 (Salmon et al., SC'11).  rk = the ten round keys (k0 + r * 0x9E3779B9, k1 + r * 0xBB67AE85), precomputed on
+// the host into the kernel parameters: they reach the XORs as uniform operands instead of costing two adds per round in
+// every thread (6 instead of 8 instructions per round).  The products stay IMAD.HI + IMAD: one IMAD.WIDE each (mul.wide.u32)
+// measured 0.5 % slower (register pairs under the 56-register cap; profiles/r02_experiments.txt).
+__device__ __forceinline__ void mul_wide(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo)
+{
+  hi = __umulhi(a, b); lo = a * b;
+}
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               uint32_t k0, uint32_t k1, uint32_t (&out)[4])
+                                               const uint32_t (&rk)[20], uint32_t (&out)[4])
 {
 #pragma unroll
   for (int r = 0; r < 10; r++) {
-    uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-    uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-    c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    uint32_t h0, l0, h1, l1;
+    mul_wide(0xD2511F53u, c0, h0, l0);
+    mul_wide(0xCD9E8D57u, c2, h1, l1);
+    c0 = h1 ^ c1 ^ rk[2 * r]; c1 = l1; c2 = h0 ^ c3 ^ rk[2 * r + 1]; c3 = l0;
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
@@ -581,7 +589,7 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
       ch.seed(v, [&](int) { return xw.next() < p.seed_cut; });
     } else {
       uint32_t att[4];
-      philox4x32_10(0x80000000u, (uint32_t)r, entry_orig, query_index, p.seed_lo, p.seed_hi, att);
+      philox4x32_10(0x80000000u, (uint32_t)r, entry_orig, query_index, p.rk, att);
       ch.seed_bits(v, att);
     }
     ch.score = ch.full_score(v);
@@ -600,8 +608,8 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
       // picks the SSE (and, hashed, the candidate), the second is the Metropolis draw
       for (int g = 0; g < SATS_K_MOVES / 4; g++) {
         uint32_t a[4], b[4];
-        philox4x32_10(2u * g + 0u, (uint32_t)r, entry_orig, query_index, p.seed_lo, p.seed_hi, a);
-        philox4x32_10(2u * g + 1u, (uint32_t)r, entry_orig, query_index, p.seed_lo, p.seed_hi, b);
+        philox4x32_10(2u * g + 0u, (uint32_t)r, entry_orig, query_index, p.rk, a);
+        philox4x32_10(2u * g + 1u, (uint32_t)r, entry_orig, query_index, p.rk, b);
         const int m = 4 * g;
         // the SSE picks depend on the draws only, not on the chains' state: issued together, off the moves' critical path
         const int i0 = pick_index(a[0], v.n1, v.pick_cut), i1 = pick_index(a[2], v.n1, v.pick_cut);

@@ -46,7 +46,7 @@ struct SatsKParams {
   int sm_team_bytes;               // total per team
   // search parameters
   int restarts, lsoln, accept_mode;
-  uint32_t seed_lo, seed_hi;
+  uint32_t rk[20];                 // Philox round keys: rk[2r] = seed_lo + r * 0x9E3779B9, rk[2r + 1] = seed_hi + r * 0xBB67AE85
   const uint32_t *accept_cut;      // [SATS_K_MOVES][SATS_K_DCLAMP + 1]: accept a move of score change -d at step m iff draw < cut
   uint32_t accept_cut0;            // the cut-off for d == 0 (unit(x) < 1.0f), the same at every step
   uint32_t seed_cut;               // validation streams: the seeding pass attempts a match iff draw < seed_cut (unit(x) < 0.5)
