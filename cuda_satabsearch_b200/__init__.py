@@ -55,6 +55,8 @@ def _load() -> C.CDLL:
         "sats_db_bootstrap": (ci, [vp, ci, C.c_uint64, ci, P(vp)]),
         "sats_db_write_ascii": (ci, [vp, cs]), "sats_db_write_packed": (ci, [vp, cs]),
         "sats_db_read_packed": (ci, [cs, P(vp)]),
+        "sats_tabcode_from_angle": (ci, [C.c_double, cs]), "sats_relative_angle": (ci, [vp, vp, vp, vp, P(C.c_double)]),
+        "sats_build_structure": (ci, [cs, ci, vp, vp, vp, P(vp)]),
         "sats_norm2": (C.c_double, [ci, ci, ci]), "sats_z_gumbel": (C.c_double, [ci, C.c_double, C.c_double]),
         "sats_pv_gumbel": (C.c_double, [C.c_double]),
         "sats_format_block": (C.c_size_t, [vp, C.c_size_t, cs, ci, cs, ci, ci, vp, vp, ci, vp, vp]),
@@ -245,6 +247,34 @@ def parse_idlist(text: bytes | str):
     buf = C.create_string_buffer(9 * cap)
     n = _check(lib().sats_idlist_parse(b, len(b), buf, cap))
     return [buf.raw[9 * k:9 * k + 9].split(b"\0")[0].decode() for k in range(n)]
+
+
+def tabcode_from_angle(omega: float) -> str:
+    """scripts/pttableau.py angle_to_tabcode; raises SatsError where the reference raises ValueError."""
+    buf = C.create_string_buffer(3)
+    _check(lib().sats_tabcode_from_angle(float(omega), buf))
+    return buf.value.decode()
+
+
+def relative_angle(c_self, d_self, c_other, d_other):
+    """scripts/ptnode.py PTNode.relative_angle on (centroid, direction cosines) axes; None where the reference gives None."""
+    a = [np.ascontiguousarray(x, np.float64) for x in (c_self, d_self, c_other, d_other)]
+    om = C.c_double(0.0)
+    rc = _check(lib().sats_relative_angle(*(x.ctypes.data for x in a), C.byref(om)))
+    return None if rc == 1 else om.value
+
+
+def build_structure(name: str, sse_types, centroids, dircos) -> Database:
+    """A one-structure Database (usable as a query) from fitted SSE axes: tableau codes from the pairwise interaxial angles,
+    midpoint distances rounded as the database writer does."""
+    t = np.ascontiguousarray(sse_types, np.uint8)
+    c = np.ascontiguousarray(centroids, np.float64)
+    d = np.ascontiguousarray(dircos, np.float64)
+    if c.shape != (len(t), 3) or d.shape != (len(t), 3):
+        raise SatsError("centroids and dircos must be (n, 3) arrays matching sse_types")
+    h = C.c_void_p()
+    _check(lib().sats_build_structure(name.encode(), len(t), t.ctypes.data, c.ctypes.data, d.ctypes.data, C.byref(h)))
+    return Database(h.value)
 
 
 def norm2(score, n1, n2):

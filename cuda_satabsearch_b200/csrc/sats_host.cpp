@@ -548,6 +548,121 @@ try {
 }
 SATS_CATCH_ALL
 
+// ------------------------------------------------------------------------------------------ query construction
+// scripts/pttableau.py:434-469 (angle_to_tabcode): the double quadrant encoding, every interval half-open on the left.
+// Angles outside (-pi, pi] and NaN raise ValueError there; here they return SATS_ERR_ARG.
+extern "C" int sats_tabcode_from_angle(double omega, char code[3])
+{
+  if (!code) return sats_fail(SATS_ERR_ARG, "sats_tabcode_from_angle: null argument");
+  const double pi = M_PI;
+  char a, b;
+  if (omega > -pi / 4 && omega <= pi / 4) a = 'P';                                                       // parallel
+  else if (omega > pi / 4 && omega <= 3 * pi / 4) a = 'R';                                               // crossing-right
+  else if ((omega > 3 * pi / 4 && omega <= pi) || (omega > -pi && omega <= -3 * pi / 4)) a = 'O';        // antiparallel
+  else if (omega > -3 * pi / 4 && omega <= -pi / 4) a = 'L';                                             // crossing-left
+  else return sats_fail(SATS_ERR_ARG, "bad omega value %g", omega);
+  if (omega > 0 && omega <= pi / 2) b = 'D';                                                             // dinner
+  else if (omega > pi / 2 && omega <= pi) b = 'T';                                                       // tea
+  else if (omega > -pi && omega <= -pi / 2) b = 'S';                                                     // supper
+  else if (omega > -pi / 2 && omega <= 0) b = 'E';                                                       // elevenses
+  else return sats_fail(SATS_ERR_ARG, "bad omega value %g", omega);
+  code[0] = a; code[1] = b; code[2] = 0;
+  return SATS_OK;
+}
+
+namespace {
+struct V3 { double x, y, z; };
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 axpy(V3 p, double s, V3 d) { return {p.x + s * d.x, p.y + s * d.y, p.z + s * d.z}; }
+inline double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline V3 unit(V3 a) { const double n = std::sqrt(dot(a, a)); return {a.x / n, a.y / n, a.z / n}; }
+inline bool tiny(V3 a, double eps) { return std::fabs(a.x) < eps && std::fabs(a.y) < eps && std::fabs(a.z) < eps; }
+}  // namespace
+
+// scripts/ptnode.py:752-880 (PTNode.relative_angle) with scripts/geometry.py:18-79 (LineLineIntersect, Bourke's shortest
+// line between two lines): the interaxial angle omega in (-pi, pi] of the axis of `self` (centroid c_self, direction cosines
+// d_self) and the axis of the other SSE, looking along their common perpendicular.  Returns 1 (and leaves *omega alone) where
+// the reference returns None: degenerate axis or no unique common perpendicular (parallel axes).
+extern "C" int sats_relative_angle(const double c_self[3], const double d_self[3], const double c_other[3],
+                                   const double d_other[3], double *omega)
+{
+  if (!c_self || !d_self || !c_other || !d_other || !omega) return sats_fail(SATS_ERR_ARG, "sats_relative_angle: null argument");
+  const double ALPHA = 100.0, EPS = 1.0e-08;            // ptnode.py:43, geometry.py:47
+  const V3 cs{c_self[0], c_self[1], c_self[2]}, ds{d_self[0], d_self[1], d_self[2]};
+  const V3 co{c_other[0], c_other[1], c_other[2]}, dother{d_other[0], d_other[1], d_other[2]};
+  const V3 p1 = co, p2 = axpy(co, ALPHA, dother);          // pa: a second point on the other SSE's axis
+  const V3 p3 = cs, p4 = axpy(cs, ALPHA, ds);          // pd: a second point on this SSE's axis
+  const V3 p13 = p1 - p3, p43 = p4 - p3;
+  if (tiny(p43, EPS)) return 1;
+  const V3 p21 = p2 - p1;
+  if (tiny(p21, EPS)) return 1;
+  const double d1343 = dot(p13, p43), d4321 = dot(p43, p21), d1321 = dot(p13, p21), d4343 = dot(p43, p43), d2121 = dot(p21, p21);
+  const double denom = d2121 * d4343 - d4321 * d4321;
+  if (std::fabs(denom) < EPS) return 1;
+  const double numer = d1343 * d4321 - d1321 * d4343;
+  const double mua = numer / denom, mub = (d1343 + d4321 * mua) / d4343;
+  const V3 pb = axpy(p1, mua, p21), pc = axpy(p3, mub, p43);
+  const V3 v1 = pb - p2, v2 = pc - pb, v3 = p4 - pc;
+  const V3 n1 = unit(cross(v1, v2)), n2 = unit(cross(v2, v3));
+  double c = dot(n1, n2);
+  if (1.0 < c) c = 1.0;             // python's min(c, 1) / max(c, -1): a NaN passes through
+  if (-1.0 > c) c = -1.0;
+  double om = std::acos(c);
+  if (dot(v2, cross(n1, n2)) < 0) om = -om;
+  *omega = om;
+  return SATS_OK;
+}
+
+// A structure from SSE axes: compute_tableau (scripts/pttableau.py:470-520, use_hk = False as in the search databases) and
+// compute_sse_midpoint_dist_matrix (scripts/ptdistmatrix.py:1014-1066), then the writer's conventions -- "%6.3f" text that the
+// search program reads back with strtof (scripts/convdb2.py:213-231), NaN -> 0.000, distances above 99.9 A clamped to 99.9
+// (scripts/pytableaucreate.py:114-116; wider values break the 7-column format).
+extern "C" int sats_build_structure(const char *name, int n, const uint8_t *sse_type, const double *centroid,
+                                    const double *dircos, sats_db **out)
+try {
+  if (!name || !sse_type || !centroid || !dircos || !out) return sats_fail(SATS_ERR_ARG, "sats_build_structure: null argument");
+  if (n < 1 || n > SATS_MAXDIM) return sats_fail(SATS_ERR_ARG, "sats_build_structure: order %d outside 1..%d", n, SATS_MAXDIM);
+  std::vector<uint8_t> tab((size_t)n * (n + 1) / 2);
+  std::vector<float> dm(tab.size());
+  auto as_written = [](double d) {
+    if (std::isnan(d)) d = 0.0;
+    if (d > 99.9) d = 99.9;
+    char buf[64];
+    snprintf(buf, sizeof buf, "%6.3f", d);
+    return strtof(buf, nullptr);
+  };
+  for (int i = 0; i < n; i++) {
+    if (sse_type[i] > 3) return sats_fail(SATS_ERR_ARG, "sats_build_structure: SSE %d has type %d (0 strand, 1 alpha, 2 pi, 3 3-10)", i, sse_type[i]);
+    tab[(size_t)i * (i + 1) / 2 + i] = sse_type[i];
+    dm[(size_t)i * (i + 1) / 2 + i] = (float)sse_type[i];
+  }
+  for (int i = 0; i < n; i++)
+    for (int j = i + 1; j < n; j++) {
+      double omega = 0.0;
+      int code = 0x44;                                         // "??": no angle (the reference leaves the entry unset)
+      const int rc = sats_relative_angle(centroid + 3 * i, dircos + 3 * i, centroid + 3 * j, dircos + 3 * j, &omega);
+      if (rc < 0) return rc;
+      if (rc == 0) {
+        char c2[3];
+        if (sats_tabcode_from_angle(omega, c2) != SATS_OK) {
+          fprintf(stderr, "WARNING: catch bad tableau angle, seting Parallel (%d,%d)\n", i, j);      // pttableau.py:497-499
+          c2[0] = 'P'; c2[1] = 'E';
+        }
+        if (tableau_code(c2[0], c2[1], &code)) return SATS_ERR_PARSE;
+      }
+      const double dx = centroid[3 * i] - centroid[3 * j], dy = centroid[3 * i + 1] - centroid[3 * j + 1],
+                   dz = centroid[3 * i + 2] - centroid[3 * j + 2];
+      tab[(size_t)j * (j + 1) / 2 + i] = (uint8_t)code;
+      dm[(size_t)j * (j + 1) / 2 + i] = as_written(std::sqrt(dx * dx + dy * dy + dz * dz));
+    }
+  std::unique_ptr<sats_db> db(new sats_db());
+  db->append(name, n, tab.data(), dm.data());
+  *out = db.release();
+  return SATS_OK;
+}
+SATS_CATCH_ALL
+
 // ------------------------------------------------------------------------------------------ statistics
 extern "C" {
 const double sats_gumbel_a = 0.3780327676087335;

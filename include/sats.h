@@ -100,6 +100,26 @@ int sats_db_write_ascii(const sats_db *db, const char *path);
 int sats_db_write_packed(const sats_db *db, const char *path);
 int sats_db_read_packed(const char *path, sats_db **out);
 
+/* ---- query construction (replaces the pure core of scripts/pytableaucreate.py) -----------------------------
+ * The PDB / DSSP front end of the reference's scripts (Bio.PDB, axis fitting) stays outside this library; these three
+ * functions turn fitted SSE axes into a searchable structure.
+ *   sats_tabcode_from_angle  angle_to_tabcode (scripts/pttableau.py:434-469): omega in (-pi, pi] -> "PE", "OT", ...; every
+ *                            interval is half-open on the left; out of range / NaN (ValueError there) -> SATS_ERR_ARG
+ *   sats_relative_angle      PTNode.relative_angle (scripts/ptnode.py:752-880) over LineLineIntersect (scripts/geometry.py:
+ *                            18-79): interaxial angle of two axes given as (centroid, direction cosines); returns 1 where
+ *                            the reference returns None (parallel or degenerate axes), 0 with *omega set otherwise
+ *   sats_build_structure     compute_tableau (scripts/pttableau.py:470-520, use_hk = False) + compute_sse_midpoint_dist_matrix
+ *                            (scripts/ptdistmatrix.py:1014-1066) for n SSEs of type sse_type[i] (0 strand, 1 alpha, 2 pi,
+ *                            3 3-10 helix), centroid / dircos = n x 3 doubles: codes from the pairwise angles ("??" where
+ *                            there is none, "PE" with a warning for a NaN angle), midpoint distances rounded through
+ *                            "%6.3f" as the writer does (scripts/convdb2.py:225; > 99.9 clamped as
+ *                            scripts/pytableaucreate.py:114-116).  The result is a one-structure sats_db, usable as a query. */
+int sats_tabcode_from_angle(double omega, char code[3]);
+int sats_relative_angle(const double c_self[3], const double d_self[3], const double c_other[3],
+                        const double d_other[3], double *omega);
+int sats_build_structure(const char *name, int n, const uint8_t *sse_type, const double *centroid,
+                         const double *dircos, sats_db **out);
+
 /* ---- Gumbel statistics (replaces gumbelstats.h:27-39) ----------------------------------------- */
 extern const double sats_gumbel_a;   /* gumbelstats.h:27 */
 extern const double sats_gumbel_b;   /* gumbelstats.h:28 */

@@ -18,7 +18,6 @@ import json
 import math
 import re
 import sys
-import textwrap
 from pathlib import Path
 
 import numpy as np
@@ -67,8 +66,8 @@ def cut(path, start_pat, end_pat, dedent=0):
     lines = path.read_text().split("\n")
     a = next(i for i, l in enumerate(lines) if re.match(start_pat, l))
     b = next(i for i in range(a + 1, len(lines)) if re.match(end_pat, lines[i]))
-    src = "\n".join(l[dedent:] if l.strip() else "" for l in lines[a:b + 1])
-    return textwrap.dedent(src) if dedent else src
+    pad = " " * dedent
+    return "\n".join(l[dedent:] if l.startswith(pad) else l for l in lines[a:b + 1])     # column-0 comment lines stay comments
 
 
 ns = {"pi": math.pi, "acos": math.acos, "alltrue": np.all, "less": np.less, "abs": np.abs, "Vector": Vector, "ALPHA": 100,
