@@ -108,32 +108,36 @@ def stratified_sample(S, db, count):
     return db.select(idx)
 
 
+def _reference_processes(td, procs, per_proc):
+    """Runs `cudaSaTabsearch_ref -c` once per prepared input file in `td`, side by side.  Returns (structures/s, detail):
+    the rate counts every process's structures against the SLOWEST process's own 'host execution time'."""
+    t0 = time.perf_counter()
+    ps = [subprocess.Popen([str(REF_BIN), "-c", "-r", str(RESTARTS)], stdin=open(os.path.join(td, "in%d" % p)),
+                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, cwd=td, text=True) for p in range(procs)]
+    search_ms = []
+    for pr in ps:
+        err = pr.communicate()[1]
+        if pr.returncode != 0:
+            raise RuntimeError("reference binary failed: " + err[-500:])
+        search_ms.append(sum(float(x) for x in re.findall(r"host execution time ([0-9.]+) ms", err)))
+    wall = time.perf_counter() - t0
+    slowest = max(search_ms) / 1e3            # the reference's own timer around sa_tabsearch_host (search only)
+    return per_proc * procs / slowest, {"wall_s": wall, "slowest_search_s": slowest}
+
+
 def run_reference_cpu(S, db, per_proc: int, procs: int):
-    """P independent `cudaSaTabsearch -c` processes on P shards of a size-stratified sample (the reference is single
-    threaded with a process-global drand48 stream: BASELINE.md section 3).  Returns (structures/s, detail)."""
+    """cpu_baseline leg of our own arm: P independent `cudaSaTabsearch -c` processes on P shards of a size-stratified
+    sample (the reference is single threaded with a process-global drand48 stream: BASELINE.md section 3)."""
     sample = stratified_sample(S, db, per_proc * procs)
     qs = query_db(S)
     with tempfile.TemporaryDirectory() as td:
-        ps = []
         qs.write_ascii(os.path.join(td, "q.ascii"))
         qtext = Path(td, "q.ascii").read_text()
         for p in range(procs):
             shard = sample.select(np.arange(p, per_proc * procs, procs, dtype=np.int32))
             shard.write_ascii(os.path.join(td, "db%d.ascii" % p))
             Path(td, "in%d" % p).write_text("db%d.ascii\nT T F\n%s" % (p, qtext))
-        t0 = time.perf_counter()
-        for p in range(procs):
-            ps.append(subprocess.Popen([str(REF_BIN), "-c", "-r", str(RESTARTS)], stdin=open(os.path.join(td, "in%d" % p)),
-                                       stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, cwd=td, text=True))
-        search_ms = []
-        for pr in ps:
-            err = pr.communicate()[1]
-            if pr.returncode != 0:
-                raise RuntimeError("reference binary failed: " + err[-500:])
-            search_ms.append(sum(float(x) for x in re.findall(r"host execution time ([0-9.]+) ms", err)))
-        wall = time.perf_counter() - t0
-    slowest = max(search_ms) / 1e3            # the reference's own timer around sa_tabsearch_host (search only)
-    return per_proc * procs / slowest, {"wall_s": wall, "slowest_search_s": slowest}
+        return _reference_processes(td, procs, per_proc)
 
 
 def run_reference_gpu(S, db, count: int):
@@ -169,32 +173,65 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def bootstrap_picks(n_src: int, orders: np.ndarray, count: int, seed: int):
+    """The synthetic database of SURVEY 8(d) without the product library: the same xorshift64* draws and the same stable
+    sort by order as sats_db_bootstrap (csrc/sats_host.cpp), so the reference arm searches the very structures our arm
+    does.  Returns (source entry per synthetic entry, name number per synthetic entry)."""
+    mask = (1 << 64) - 1
+    x = seed or 0x9E3779B97F4A7C15
+    pick = np.empty(count, np.int64)
+    for k in range(count):
+        x ^= x >> 12
+        x ^= (x << 25) & mask
+        x ^= x >> 27
+        pick[k] = (((x * 0x2545F4914F6CDD1D) & mask) >> 33) % n_src
+    pos = np.argsort(orders[pick], kind="stable")
+    return pick[pos], pos
+
+
 def reference_arm(args):
+    """The reference's own `-c` CPU path on all host cores.  Nothing of the product is loaded in this process: the
+    synthetic db is re-derived with numpy (bootstrap_picks) from the committed 586-structure fixture and written with the
+    test-side ASCII writer (tests/_refio.py)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import cuda_satabsearch_b200 as S
     if not REF_BIN.exists():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/cudaSaTabsearch_ref not built"}))
         return
-    db = synthetic_db(S)
+    sys.path.insert(0, str(ROOT / "tests"))
+    from _refio import Structure, read_packed, write_ascii_db, write_query_input
+    base = read_packed(ROOT / "tests" / "golden" / "small586.satsdb")
+    query = {s.name: s for s in read_packed(ROOT / "tests" / "golden" / "queries.satsdb")}[QUERY]
+    src, num = bootstrap_picks(len(base), np.array([s.n for s in base]), DB_SIZE, DB_SEED)
     cores = host_cores()
-    per_proc = 600                       # ~1.7 s of single-core work per process per step
+    per_proc = 600                       # ~0.7 s of single-core work per process per step
+    sample = np.linspace(0, DB_SIZE - 1, per_proc * cores).round().astype(np.int64)       # size-stratified
     vals = []
-    for it in range(args.warmup + args.steps):
-        v, _ = run_reference_cpu(S, db, per_proc, cores)
-        if it >= args.warmup:
-            vals.append(v)
+    with tempfile.TemporaryDirectory() as td:
+        for p in range(cores):
+            ents = [Structure("s%06d" % (num[k] % 1000000), base[src[k]].tab, base[src[k]].dmat) for k in sample[p::cores]]
+            write_ascii_db(os.path.join(td, "db%d.ascii" % p), ents)
+            write_query_input(os.path.join(td, "in%d" % p), "db%d.ascii" % p, True, False, [query])
+        for it in range(args.warmup + args.steps):
+            v, _ = _reference_processes(td, cores, per_proc)
+            if it >= args.warmup:
+                vals.append(v)
     value = float(np.mean(vals))
-    sample = ("%d processes x %d structures (size-stratified sample of the 100k synthetic db), reference -c path, "
-              "rate = structures / slowest process's own 'host execution time'" % (cores, per_proc))
+    sample_txt = ("%d processes x %d structures (size-stratified sample of the 100k synthetic db), reference -c path, "
+                  "rate = structures / slowest process's own 'host execution time'" % (cores, per_proc))
+    full = None
+    fj = ROOT / "profiles" / "r02_reference_full100k.json"
+    if fj.exists():                      # one recorded run of the WHOLE 100k db (P shards, slowest), pinning the extrapolation
+        full = json.loads(fj.read_text())
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "structures/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * per_proc * cores / value,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic",
         "config": CONFIG, "move_evals_per_s": value * RESTARTS * MOVES,
-        "cpu_baseline": {"value": value, "unit": "structures/s", "cores": cores, "kind": "reference", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "structures/s", "cores": cores, "kind": "reference", "sample": sample_txt},
         "e2e": {"value": value, "unit": "structures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "recorded_full_db_run": full,
     }
     print(json.dumps(line))
 

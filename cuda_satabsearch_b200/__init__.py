@@ -68,6 +68,8 @@ def _load() -> C.CDLL:
         "sats_search_upload": (ci, [vp, vp, ci, ci]),
         "sats_search_launch": (ci, [vp, P(Params), C.c_uint32, P(C.c_float)]),
         "sats_search_collect": (ci, [vp, vp, vp]), "sats_searcher_sync": (ci, [vp]),
+        "sats_search_collect_begin": (ci, [vp]),
+        "sats_search_device_results": (ci, [vp, P(vp), P(ci), P(ci), vp]), "sats_searcher_entry_index": (ci, [vp, vp]),
         "sats_searcher_launch_count": (C.c_longlong, [vp]),
         "sats_searcher_get_xorwow": (ci, [vp, vp]), "sats_searcher_reset_xorwow": (ci, [vp, C.c_uint64]),
         "sats_device_count": (ci, []),
@@ -371,6 +373,24 @@ class Searcher:
 
     def sync(self):
         _check(lib().sats_searcher_sync(self._h))
+
+    def collect_begin(self):
+        _check(lib().sats_search_collect_begin(self._h))
+
+    def device_results(self):
+        """After launch(): (device pointer to int32 [qcount, entries] in device order, qcount, entries, slot -> batch position).
+        For gathering shards with a collective; sync() first (the results are produced on the searcher's own stream)."""
+        ptr = C.c_void_p()
+        q, e = C.c_int(0), C.c_int(0)
+        slots = np.zeros(max(1, getattr(self, "_qcount", 1)), np.int32)
+        _check(lib().sats_search_device_results(self._h, C.byref(ptr), C.byref(q), C.byref(e), slots.ctypes.data))
+        return ptr.value, q.value, e.value, slots[:q.value]
+
+    def entry_index(self) -> np.ndarray:
+        """Original db index of every resident entry, in device order (decreasing structure order)."""
+        idx = np.zeros(max(1, self.entries), np.int32)
+        _check(lib().sats_searcher_entry_index(self._h, idx.ctypes.data))
+        return idx[:self.entries]
 
     def topk(self, k: int):
         """After launch(): device-side selection -> (index int32 [q, k] original db indices, scores int32 [q, k])."""

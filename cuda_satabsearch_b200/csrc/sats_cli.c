@@ -26,6 +26,7 @@
  *             (selected on the device with sats_search_hits); LSOLN = F, not together with -k
  */
 #include <getopt.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -46,6 +47,16 @@ static void die(const char *what)
 {
   fprintf(stderr, "%s: %s\n", what, sats_last_error());
   exit(1);
+}
+
+/* one searcher per GPU, created side by side: each builds and uploads its own part of the database */
+typedef struct { const sats_db *db; int device, rank, count, rc; sats_searcher *sr; char err[512]; } create_job;
+static void *create_worker(void *arg)
+{
+  create_job *j = (create_job *)arg;
+  j->rc = sats_searcher_create(j->db, j->device, j->rank, j->count, &j->sr);
+  if (j->rc != SATS_OK) { strncpy(j->err, sats_last_error(), sizeof j->err - 1); j->err[sizeof j->err - 1] = 0; }   /* the message is thread-local */
+  return NULL;
 }
 
 /* one selected row while the shards' hit lists are merged */
@@ -211,8 +222,21 @@ int main(int argc, char *argv[])
   fprintf(stderr, "Copying database to device...\n");
   t0 = now_ms();
   sats_searcher *sr[MAX_GPUS];
-  for (int g = 0; g < ngpus; g++)
-    if (sats_searcher_create(db, g % have, split_blocks ? 0 : g, split_blocks ? 1 : ngpus, &sr[g]) != SATS_OK) die("ERROR creating searcher");
+  {
+    create_job jobs[MAX_GPUS];
+    pthread_t tid[MAX_GPUS];
+    for (int g = 0; g < ngpus; g++) {
+      jobs[g].db = db; jobs[g].device = g % have; jobs[g].rank = split_blocks ? 0 : g; jobs[g].count = split_blocks ? 1 : ngpus;
+      jobs[g].sr = NULL; jobs[g].rc = SATS_OK; jobs[g].err[0] = 0;
+      if (g > 0 && pthread_create(&tid[g], NULL, create_worker, &jobs[g]) != 0) { fprintf(stderr, "ERROR starting a worker thread\n"); exit(1); }
+    }
+    create_worker(&jobs[0]);
+    for (int g = 1; g < ngpus; g++) pthread_join(tid[g], NULL);
+    for (int g = 0; g < ngpus; g++) {
+      if (jobs[g].rc != SATS_OK) { fprintf(stderr, "ERROR creating searcher: %s\n", jobs[g].err); exit(1); }
+      sr[g] = jobs[g].sr;
+    }
+  }
   fprintf(stderr, "Copied %d entries to %d GPU(s) in %f ms\n", dbsize, ngpus, now_ms() - t0);
 
   sats_params prm;
@@ -286,6 +310,8 @@ int main(int argc, char *argv[])
         }
         free(cand); free(g_idx); free(g_sc); free(all_idx); free(all_sc);
       } else {
+        for (int g = 0; g < ngpus; g++)          /* every GPU's copy in flight before the first wait */
+          if (sats_search_collect_begin(sr[g]) != SATS_OK) die("ERROR collecting results");
         for (int g = 0; g < ngpus; g++)
           if (sats_search_collect(sr[g], scores, maps) != SATS_OK) die("ERROR collecting results");
       }

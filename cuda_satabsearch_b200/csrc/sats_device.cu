@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -157,6 +158,7 @@ struct sats_searcher {
   int32_t *h_scores = nullptr; int8_t *h_maps = nullptr;
   size_t score_cap = 0, map_cap = 0;
   int last_q = 0, last_lsoln = 0;
+  bool collect_pending = false;           // sats_search_collect_begin() has enqueued the copies of the last launch
   int32_t *d_topk = nullptr, *h_topk = nullptr; size_t topk_cap = 0;
   int32_t *d_sorted_order = nullptr;      // order of every resident entry, device order (for sats_search_hits)
   int32_t *d_hits = nullptr, *h_hits = nullptr; size_t hits_cap = 0;
@@ -248,7 +250,9 @@ try {
     total += bytes[k];
   }
   std::vector<uint8_t> blobs(total ? total : 16, 0);
-  for (size_t k = 0; k < local.size(); k++) {
+  // the blobs are independent: fill them on a few host threads (100 k structures = 240 MB of cells)
+  auto fill_range = [&](size_t k0, size_t k1) {
+  for (size_t k = k0; k < k1; k++) {
     int e = s->sorted_orig[k], n = db->order[e];
     uint8_t *b = blobs.data() + off[k];
     int32_t hdr[4] = {n, e, 0, 0};
@@ -260,6 +264,21 @@ try {
     // addresses a row whose gate never opens without any special casing in the kernel
     for (int j = 0; j < n; j++) { const uint32_t nan_cell[2] = {0x7fc00000u, 0u}; memcpy(b + SATS_K_ENTRY_HDR + 8 * (size_t)j, nan_cell, 8); }
     fill_cells(db, e, b + SATS_K_ENTRY_HDR + 8 * (size_t)n);
+  }
+  };
+  {
+    const size_t nthreads = total < (8u << 20) ? 1 : std::max<size_t>(1, std::min<size_t>(8, std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    size_t k0 = 0;
+    for (size_t t = 0; t < nthreads; t++) {          // equal BYTES per thread (the list is sorted by decreasing size)
+      size_t k1 = k0;
+      const uint64_t upto = total / nthreads * (t + 1);
+      while (k1 < local.size() && (t + 1 == nthreads || off[k1] < upto)) k1++;
+      if (t + 1 == nthreads) fill_range(k0, local.size());
+      else pool.emplace_back(fill_range, k0, k1);
+      k0 = k1;
+    }
+    for (auto &th : pool) th.join();
   }
   auto fail = [&](int rc) { sats_searcher_free(s); return rc; };
 #define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(sats_fail(SATS_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_))); } while (0)
@@ -485,6 +504,7 @@ try {
   rc = ensure_results(s, Q, pp->lsoln);
   if (rc) return rc;
   s->last_lsoln = pp->lsoln;
+  s->collect_pending = false;
   CK(cudaMemsetAsync(s->d_scores, 0x80, (size_t)Q * std::max(1, D) * 4, s->stream));
   if (elapsed_ms) CK(cudaEventRecord(s->ev0, s->stream));
 
@@ -689,6 +709,22 @@ try {
 }
 SATS_CATCH_ALL
 
+// enqueue the device -> pinned host copies of the last launch's results (no wait): lets a multi-GPU caller start every
+// GPU's copy before it waits for the first
+extern "C" int sats_search_collect_begin(sats_searcher *s)
+try {
+  if (!s) return sats_fail(SATS_ERR_ARG, "sats_search_collect_begin: null argument");
+  CK(cudaSetDevice(s->device));
+  const int D = (int)s->sorted_orig.size(), Q = s->last_q;
+  if (D == 0 || Q < 1) return SATS_OK;
+  size_t n = (size_t)Q * D;
+  CK(cudaMemcpyAsync(s->h_scores, s->d_scores, n * 4, cudaMemcpyDeviceToHost, s->stream));
+  if (s->last_lsoln) CK(cudaMemcpyAsync(s->h_maps, s->d_maps, n * SATS_K_MAPROW, cudaMemcpyDeviceToHost, s->stream));
+  s->collect_pending = true;
+  return SATS_OK;
+}
+SATS_CATCH_ALL
+
 extern "C" int sats_search_collect(sats_searcher *s, int32_t *scores, int32_t *maps)
 try {
   if (!s || !scores) return sats_fail(SATS_ERR_ARG, "sats_search_collect: null argument");
@@ -696,9 +732,8 @@ try {
   CK(cudaSetDevice(s->device));
   const int D = (int)s->sorted_orig.size(), Q = s->last_q;
   if (D == 0) return SATS_OK;
-  size_t n = (size_t)Q * D;
-  CK(cudaMemcpyAsync(s->h_scores, s->d_scores, n * 4, cudaMemcpyDeviceToHost, s->stream));
-  if (s->last_lsoln) CK(cudaMemcpyAsync(s->h_maps, s->d_maps, n * SATS_K_MAPROW, cudaMemcpyDeviceToHost, s->stream));
+  if (!s->collect_pending) { int rc = sats_search_collect_begin(s); if (rc) return rc; }
+  s->collect_pending = false;
   CK(cudaStreamSynchronize(s->stream));
   for (int q = 0; q < Q; q++) {
     const int n1 = s->q_n1[q];
@@ -717,6 +752,25 @@ try {
   return SATS_OK;
 }
 SATS_CATCH_ALL
+
+// Results of the last launch where they are: for callers that gather the shards' scores with their own collective (NCCL)
+extern "C" int sats_search_device_results(sats_searcher *s, const int32_t **d_scores, int *qcount, int *entries, int32_t *slot_query)
+{
+  if (!s || !d_scores) return sats_fail(SATS_ERR_ARG, "sats_search_device_results: null argument");
+  if (s->last_q < 1 || !s->d_scores) return sats_fail(SATS_ERR_ARG, "sats_search_device_results: no search has been launched");
+  *d_scores = s->d_scores;
+  if (qcount) *qcount = s->last_q;
+  if (entries) *entries = (int)s->sorted_orig.size();
+  if (slot_query) for (int q = 0; q < s->last_q; q++) slot_query[q] = s->slot_q[q];
+  return SATS_OK;
+}
+
+extern "C" int sats_searcher_entry_index(const sats_searcher *s, int32_t *index)
+{
+  if (!s || !index) return sats_fail(SATS_ERR_ARG, "sats_searcher_entry_index: null argument");
+  for (size_t k = 0; k < s->sorted_orig.size(); k++) index[k] = s->sorted_orig[k];
+  return SATS_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ top-k
 // One CTA per query slot selects the k best-scoring entries of that query on the device, so only k (position, score)

@@ -191,8 +191,11 @@ __device__ __forceinline__ void mul_wide(uint32_t a, uint32_t b, uint32_t &hi, u
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                const uint32_t (&rk)[20], uint32_t (&out)[4])
 {
+#ifndef SATS_EXP_ROUNDS
+#define SATS_EXP_ROUNDS 10      // experiments only (profiles/r02_experiments.txt): anything else is not Philox4x32-10
+#endif
 #pragma unroll
-  for (int r = 0; r < 10; r++) {
+  for (int r = 0; r < SATS_EXP_ROUNDS; r++) {
     uint32_t h0, l0, h1, l1;
     mul_wide(0xD2511F53u, c0, h0, l0);
     mul_wide(0xCD9E8D57u, c2, h1, l1);

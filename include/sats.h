@@ -245,6 +245,17 @@ int sats_search_upload(sats_searcher *s, const sats_db *queries, int qfirst, int
 int sats_search_launch(sats_searcher *s, const sats_params *params, uint32_t query_index_base,
                        float *elapsed_ms);
 int sats_search_collect(sats_searcher *s, int32_t *scores, int32_t *maps);
+/* Multi-GPU hosts: sats_search_collect_begin() only ENQUEUES the device -> host copies (pinned staging), so that every
+ * GPU's copy is in flight before the first sats_search_collect() waits; collect without begin does both.             */
+int sats_search_collect_begin(sats_searcher *s);
+/* SURVEY 8(e) "one tiny gather after": the results where they are, for callers that gather the shards with their own
+ * collective (ncclGather / AllGather) instead of N host copies.  *d_scores = device pointer to int32 [qcount][entries]
+ * in DEVICE order (row = query slot, column = position in this searcher's decreasing-size order; entries outside the
+ * launch's pool hold 0x80808080), valid until the next upload / launch on this searcher and produced on its stream
+ * (call sats_searcher_sync() first).  slot_query (may be NULL) receives, per row, the query's position in the batch;
+ * sats_searcher_entry_index() gives, per column, the ORIGINAL db index.                                             */
+int sats_search_device_results(sats_searcher *s, const int32_t **d_scores, int *qcount, int *entries, int32_t *slot_query);
+int sats_searcher_entry_index(const sats_searcher *s, int32_t *index);
 /* after sats_search_launch(), the k best-scoring entries of every query slot, selected ON THE DEVICE
  * (exact counting select over the integer scores) so that only k (index, score) pairs per query are copied back
  * instead of one score per database entry.  Rows of k: score descending; ties by decreasing structure order, then
