@@ -72,11 +72,13 @@ def _load() -> C.CDLL:
         "sats_search_device_results": (ci, [vp, P(vp), P(ci), P(ci), vp]), "sats_searcher_entry_index": (ci, [vp, vp]),
         "sats_searcher_launch_count": (C.c_longlong, [vp]),
         "sats_searcher_get_xorwow": (ci, [vp, vp]), "sats_searcher_reset_xorwow": (ci, [vp, C.c_uint64]),
-        "sats_device_count": (ci, []),
+        "sats_device_count": (ci, []), "sats_device_init": (ci, [ci]),
         "sats_pick_boundaries": (ci, [ci, vp]), "sats_accept_cutoffs": (ci, [vp, vp]), "sats_seed_cutoff": (C.c_uint32, []),
         "sats_score_threshold": (C.c_int32, [C.c_double, ci, ci]),
         "sats_search_topk": (ci, [vp, ci, vp, vp]),
         "sats_search_hits": (ci, [vp, C.c_double, ci, vp, vp, vp]),
+        "sats_search_bind_cut": (ci, [vp, C.c_double]),
+        "sats_search_streamed_hits": (ci, [vp, ci, vp, vp, vp, P(C.c_int64)]),
         "sats_results_parse": (ci, [cs, C.c_size_t, P(vp)]), "sats_results_free": (None, [vp]),
         "sats_results_blocks": (ci, [vp]), "sats_results_query": (cs, [vp, ci]), "sats_results_dbfile": (cs, [vp, ci]),
         "sats_results_flags": (ci, [vp, ci, P(ci)]), "sats_results_rows": (ci, [vp, ci]),
@@ -409,6 +411,20 @@ class Searcher:
         sc = np.full((q, cap), np.iinfo(np.int32).min, np.int32)
         _check(lib().sats_search_hits(self._h, float(z_min), cap, cnt.ctypes.data, idx.ctypes.data, sc.ctypes.data))
         return cnt, idx, sc
+
+    def bind_cut(self, z_min: float | None):
+        """Streaming hits: from now on every launch appends its hits (z-score >= z_min) to a device list; None unbinds."""
+        _check(lib().sats_search_bind_cut(self._h, float("nan") if z_min is None else float(z_min)))
+
+    def streamed_hits(self, cap: int):
+        """After a launch with a bound cut: (counts, index, scores, d2h_bytes) -- the first three exactly as hits()."""
+        q = self._qcount
+        cnt = np.zeros(q, np.int32)
+        idx = np.full((q, cap), -1, np.int32)
+        sc = np.full((q, cap), np.iinfo(np.int32).min, np.int32)
+        nbytes = C.c_int64(0)
+        _check(lib().sats_search_streamed_hits(self._h, cap, cnt.ctypes.data, idx.ctypes.data, sc.ctypes.data, C.byref(nbytes)))
+        return cnt, idx, sc, nbytes.value
 
     def xorwow_states(self) -> np.ndarray:
         st = np.zeros((128 * 128, 6), np.uint32)

@@ -22,8 +22,9 @@
  *   -L        also search database structures of order 112..128 (the reference drops everything above 111)
  *   -k N      print only the N best-scoring structures of each (query, pool) block, best first (selected on the
  *             device with sats_search_topk, so only N rows per query leave each GPU); LSOLN = F
- *   -z Z      print only the structures whose z-score (4th column) is >= Z, in database order of decreasing size
- *             (selected on the device with sats_search_hits); LSOLN = F, not together with -k
+ *   -z Z      print only the structures whose z-score (4th column) is >= Z, in database order of decreasing size.  The
+ *             cut is bound to the searchers (sats_search_bind_cut), so the kernels stream the hits into a device list
+ *             while they run and only the hits are copied back (bytes reported on stderr); LSOLN = F, not together with -k
  */
 #include <getopt.h>
 #include <pthread.h>
@@ -225,6 +226,11 @@ int main(int argc, char *argv[])
   {
     create_job jobs[MAX_GPUS];
     pthread_t tid[MAX_GPUS];
+    /* contexts one after the other (the driver serialises their creation and concurrent attempts are slower), then
+     * the searchers -- blob build + upload -- side by side */
+    for (int g = 0; g < ngpus && g < have; g++)
+      if (sats_device_init(g) != SATS_OK) die("ERROR initialising device");
+    fprintf(stderr, "Initialised %d device context(s) in %f ms\n", ngpus < have ? ngpus : have, now_ms() - t0);
     for (int g = 0; g < ngpus; g++) {
       jobs[g].db = db; jobs[g].device = g % have; jobs[g].rank = split_blocks ? 0 : g; jobs[g].count = split_blocks ? 1 : ngpus;
       jobs[g].sr = NULL; jobs[g].rc = SATS_OK; jobs[g].err[0] = 0;
@@ -267,6 +273,7 @@ int main(int argc, char *argv[])
       for (int g = 0; g < ngpus; g++)
         if (sats_search_upload(sr[g], queries, q0, nq) != SATS_OK) die("ERROR uploading queries");
       for (int g = 0; g < ngpus; g++) {
+        if (zcut && sats_search_bind_cut(sr[g], zmin) != SATS_OK) die("ERROR binding the significance cut");
         if (split_blocks) { prm.grid_rank = g; prm.grid_count = ngpus; }
         if (sats_search_launch(sr[g], &prm, (uint32_t)q0, NULL) != SATS_OK) die("kernel launch failed");
       }
@@ -289,7 +296,12 @@ int main(int argc, char *argv[])
         if (!cand || !g_idx || !g_sc || !all_idx || !all_sc) { fprintf(stderr, "malloc failed\n"); exit(1); }
         for (int g = 0; g < ngpus; g++) {
           if (topk > 0) { if (sats_search_topk(sr[g], topk, g_idx, g_sc) != SATS_OK) die("ERROR selecting top hits"); }
-          else if (sats_search_hits(sr[g], zmin, hcap, top_n, g_idx, g_sc) != SATS_OK) die("ERROR selecting significant hits");
+          else {
+            int64_t nbytes = 0;
+            if (sats_search_streamed_hits(sr[g], hcap, top_n, g_idx, g_sc, &nbytes) != SATS_OK) die("ERROR selecting significant hits");
+            fprintf(stderr, "GPU %d streamed its hits: %lld bytes device -> host for %d queries (%f per query; the dense scores would be %lld)\n",
+                    g, (long long)nbytes, nq, (double)nbytes / nq, (long long)nq * (long long)sats_searcher_entry_count(sr[g]) * 4);
+          }
           memcpy(all_idx + (size_t)g * nq * hcap, g_idx, sizeof(int32_t) * (size_t)nq * (size_t)hcap);
           memcpy(all_sc + (size_t)g * nq * hcap, g_sc, sizeof(int32_t) * (size_t)nq * (size_t)hcap);
         }

@@ -162,6 +162,13 @@ struct sats_searcher {
   int32_t *d_topk = nullptr, *h_topk = nullptr; size_t topk_cap = 0;
   int32_t *d_sorted_order = nullptr;      // order of every resident entry, device order (for sats_search_hits)
   int32_t *d_hits = nullptr, *h_hits = nullptr; size_t hits_cap = 0;
+  // streaming hits: a bound significance cut makes every launch append its hits to d_stream_list (see SatsKParams)
+  bool cut_bound = false; double cut_z = 0.0;
+  int32_t *d_stream_thr = nullptr; size_t stream_thr_cap = 0;      // [query slot][SATS_MAXDIM_EXT + 1]
+  unsigned *d_stream_cursor = nullptr;
+  int4 *d_stream_list = nullptr; size_t stream_list_cap = 0;
+  int4 *h_stream = nullptr; size_t h_stream_cap = 0;
+  bool stream_valid = false;              // the last launch ran with the cut bound
   long long launches = 0;
   bool attr_done = false;
 };
@@ -210,6 +217,19 @@ extern "C" int sats_device_count(void)
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
+}
+
+// Creates the CUDA context of a device (cudaSetDevice + a no-op runtime call).  Context creation is serialised inside the
+// driver and SLOWER when several host threads do it at once (measured: 0.75 s + 0.23 s one after the other, 1.9 s from two
+// threads, profiles/r02_experiments.txt), so a multi-GPU host calls this for every device first, from one thread, and
+// only then builds its searchers side by side.
+extern "C" int sats_device_init(int device)
+{
+  int ndev = sats_device_count();
+  if (device < 0 || device >= ndev) return sats_fail(SATS_ERR_ARG, "device %d out of range (have %d)", device, ndev);
+  CK(cudaSetDevice(device));
+  CK(cudaFree(nullptr));
+  return SATS_OK;
 }
 
 extern "C" int sats_searcher_create(const sats_db *db, int device, int shard_rank, int shard_count, sats_searcher **out)
@@ -329,6 +349,7 @@ extern "C" void sats_searcher_free(sats_searcher *s)
   cudaFree(s->d_pool_list); cudaFree(s->d_xw_blocks); cudaFree(s->d_counters); cudaFree(s->d_qblobs); cudaFree(s->d_qoff); cudaFree(s->d_qbytes);
   cudaFree(s->d_scores); cudaFree(s->d_maps); cudaFree(s->d_topk); cudaFreeHost(s->h_topk);
   cudaFree(s->d_sorted_order); cudaFree(s->d_hits); cudaFreeHost(s->h_hits);
+  cudaFree(s->d_stream_thr); cudaFree(s->d_stream_cursor); cudaFree(s->d_stream_list); cudaFreeHost(s->h_stream);
   if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
   cudaFreeHost(s->h_qstage); cudaFreeHost(s->h_scores); cudaFreeHost(s->h_maps);
   if (s->ev0) cudaEventDestroy(s->ev0);
@@ -505,6 +526,34 @@ try {
   if (rc) return rc;
   s->last_lsoln = pp->lsoln;
   s->collect_pending = false;
+  s->stream_valid = false;
+  const int32_t *hit_thr = nullptr;
+  if (s->cut_bound) {
+    // one integer score threshold per (query slot, structure order), as in sats_search_hits(); list room for every
+    // (query, entry) pair up to 4 M hits (64 MB) -- beyond that the reader falls back to the dense post-pass
+    const int T = SATS_MAXDIM_EXT + 1;
+    std::vector<int32_t> thr((size_t)Q * T);
+    for (int q = 0; q < Q; q++)
+      for (int n2 = 0; n2 < T; n2++) thr[(size_t)q * T + n2] = n2 == 0 ? INT_MAX : sats_score_threshold(s->cut_z, s->q_n1[q], n2);
+    if (thr.size() > s->stream_thr_cap) {
+      cudaFree(s->d_stream_thr); s->d_stream_thr = nullptr; s->stream_thr_cap = 0;
+      CK(cudaMalloc(&s->d_stream_thr, thr.size() * 4));
+      s->stream_thr_cap = thr.size();
+    }
+    const size_t want = std::min<size_t>((size_t)Q * std::max(1, D), (size_t)4 << 20);
+    if (want > s->stream_list_cap) {
+      cudaFree(s->d_stream_list); s->d_stream_list = nullptr; s->stream_list_cap = 0;
+      CK(cudaMalloc(&s->d_stream_list, want * sizeof(int4)));
+      s->stream_list_cap = want;
+    }
+    if (!s->d_stream_cursor) CK(cudaMalloc(&s->d_stream_cursor, sizeof(unsigned)));
+    CK(cudaStreamSynchronize(s->stream));           // `thr` is pageable host memory
+    CK(cudaMemcpyAsync(s->d_stream_thr, thr.data(), thr.size() * 4, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemsetAsync(s->d_stream_cursor, 0, sizeof(unsigned), s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    hit_thr = s->d_stream_thr;
+    s->stream_valid = true;
+  }
   CK(cudaMemsetAsync(s->d_scores, 0x80, (size_t)Q * std::max(1, D) * 4, s->stream));
   if (elapsed_ms) CK(cudaEventRecord(s->ev0, s->stream));
 
@@ -531,6 +580,7 @@ try {
   k.temps = reinterpret_cast<const float *>(s->d_accept + (size_t)SATS_K_MOVES * (SATS_K_DCLAMP + 1));
   k.out_scores = s->d_scores; k.out_maps = pp->lsoln ? s->d_maps : nullptr; k.out_stride = std::max(1, D);
   k.xw_states = s->d_xw; k.pool_list = s->d_pool_list; k.xw_blocks = s->d_xw_blocks;
+  k.hit_thr = hit_thr; k.hit_cursor = s->d_stream_cursor; k.hit_list = s->d_stream_list; k.hit_cap = (unsigned)s->stream_list_cap;
 
   if (r1 > r0) {
     if (xorwow) {
@@ -1011,6 +1061,64 @@ try {
     for (int i = 0; i < cap; i++) {
       index_out[row * cap + i] = i < got ? s->sorted_orig[pr[2 * i]] : -1;
       score_out[row * cap + i] = i < got ? pr[2 * i + 1] : INT_MIN;
+    }
+  }
+  return SATS_OK;
+}
+SATS_CATCH_ALL
+
+// ---- streaming hits (second half) ----------------------------------------------------------------------
+extern "C" int sats_search_bind_cut(sats_searcher *s, double z_min)
+{
+  if (!s) return sats_fail(SATS_ERR_ARG, "sats_search_bind_cut: null searcher");
+  s->cut_bound = z_min == z_min;         // NaN unbinds
+  s->cut_z = z_min;
+  return SATS_OK;
+}
+
+extern "C" int sats_search_streamed_hits(sats_searcher *s, int cap, int32_t *count_out, int32_t *index_out, int32_t *score_out,
+                                         int64_t *d2h_bytes)
+try {
+  if (!s || !count_out || !index_out || !score_out || cap < 1) return sats_fail(SATS_ERR_ARG, "sats_search_streamed_hits: bad argument");
+  if (!s->stream_valid) return sats_fail(SATS_ERR_ARG, "sats_search_streamed_hits: the last launch ran without a bound cut (sats_search_bind_cut)");
+  CK(cudaSetDevice(s->device));
+  const int Q = s->last_q;
+  unsigned total = 0;
+  CK(cudaMemcpyAsync(&total, s->d_stream_cursor, sizeof total, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  if (d2h_bytes) *d2h_bytes = (int64_t)sizeof total;
+  if ((size_t)total > s->stream_list_cap) {
+    // more hits than the list holds (a cut that keeps nearly everything): the dense scores are still on the device
+    if (d2h_bytes) *d2h_bytes += (int64_t)Q * 8 + (int64_t)std::min<long long>((long long)total, (long long)Q * cap) * 8;
+    return sats_search_hits(s, s->cut_z, cap, count_out, index_out, score_out);
+  }
+  if ((size_t)total > s->h_stream_cap) {
+    cudaFreeHost(s->h_stream); s->h_stream = nullptr; s->h_stream_cap = 0;
+    CK(cudaMallocHost(&s->h_stream, (size_t)total * sizeof(int4)));
+    s->h_stream_cap = total;
+  }
+  if (total) {
+    CK(cudaMemcpyAsync(s->h_stream, s->d_stream_list, (size_t)total * sizeof(int4), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    if (d2h_bytes) *d2h_bytes += (int64_t)total * (int64_t)sizeof(int4);
+  }
+  // the kernel appends in completion order: bring every query's hits into device order (decreasing structure order, then
+  // file order) -- the order sats_search_hits() and the -z printer use
+  std::vector<std::vector<std::pair<int32_t, int32_t>>> per((size_t)Q);
+  for (unsigned k = 0; k < total; k++) {
+    const int4 h = s->h_stream[k];
+    if (h.x < 0 || h.x >= Q) return sats_fail(SATS_ERR_CUDA, "corrupt hit record");
+    per[(size_t)h.x].emplace_back(h.y, h.z);
+  }
+  for (int q = 0; q < Q; q++) {
+    auto &v = per[(size_t)q];
+    std::sort(v.begin(), v.end());
+    const size_t row = (size_t)s->slot_q[q];
+    count_out[row] = (int32_t)v.size();
+    for (int i = 0; i < cap; i++) {
+      const bool have = (size_t)i < v.size();
+      index_out[row * cap + i] = have ? s->sorted_orig[v[(size_t)i].first] : -1;
+      score_out[row * cap + i] = have ? v[(size_t)i].second : INT_MIN;
     }
   }
   return SATS_OK;

@@ -639,7 +639,13 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
   for (int w = 1; w < warps; w++) key = red[w] > key ? red[w] : key;
   const int team_best = (int)(uint32_t)(key >> 32) - 0x40000000;
   const unsigned team_tag = ~(uint32_t)key;
-  if (tl == 0) p.out_scores[(size_t)out_slot * p.out_stride + entry_sorted] = team_best;
+  if (tl == 0) {
+    p.out_scores[(size_t)out_slot * p.out_stride + entry_sorted] = team_best;
+    if (p.hit_thr != nullptr && team_best >= __ldg(p.hit_thr + out_slot * (SATS_MAXDIM_EXT + 1) + v.n2)) {
+      const unsigned pos = atomicAdd(p.hit_cursor, 1u);
+      if (pos < p.hit_cap) p.hit_list[pos] = make_int4(out_slot, entry_sorted, team_best, 0);
+    }
+  }
   if (LSOLN && best == team_best && (unsigned)best_tag == team_tag) {
     int8_t *row = p.out_maps + ((size_t)out_slot * p.out_stride + entry_sorted) * SATS_K_MAPROW;
 #pragma unroll 1

@@ -4,6 +4,7 @@
 #define SATS_KPARAMS_H
 
 #include <cstdint>
+#include <vector_types.h>
 
 #define SATS_K_MOVES 100
 #define SATS_K_DCLAMP 229          // expf(-d/T) <= 2^-33 (smallest uniform) for every d >= 229 and T <= 10
@@ -52,6 +53,12 @@ struct SatsKParams {
   uint32_t seed_cut;               // validation streams: the seeding pass attempts a match iff draw < seed_cut (unit(x) < 0.5)
   uint32_t q_index_base;           // Philox query index = q_index_base + the query's position in the batch (header word 1)
   const float *temps;              // [SATS_K_MOVES]: T_m = 10 * 0.95^m accumulated in fp32 like kernel.cu:1189
+  // streaming hits: while a significance cut is bound, the arg-max epilogue also appends every entry whose
+  // score reaches hit_thr[query slot][entry order] to one device list, so that only the hits ever travel to the host
+  const int32_t *hit_thr;          // [query slot][SATS_MAXDIM_EXT + 1], nullptr = no cut bound
+  unsigned *hit_cursor;            // hits appended so far (may run past hit_cap: the overflow is detected on the host)
+  int4 *hit_list;                  // (query slot, sorted entry index, score, 0)
+  unsigned hit_cap;
   // outputs, indexed [query slot][sorted entry index]
   int32_t *out_scores;
   int8_t *out_maps;                // rows of SATS_K_MAPROW bytes, or nullptr

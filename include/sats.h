@@ -270,6 +270,16 @@ int sats_search_topk(sats_searcher *s, int k, int32_t *index_out, int32_t *score
  * exceed cap: the first cap hits are returned); index_out / score_out: rows of cap, hits in device order (decreasing
  * structure order, then file order), ORIGINAL db indices, -1 / INT32_MIN padding.  Sharded search: one call per shard.  */
 int sats_search_hits(sats_searcher *s, double z_min, int cap, int32_t *count_out, int32_t *index_out, int32_t *score_out);
+/* SURVEY 8(f2), streaming form: bind the cut BEFORE launching and the kernel itself appends every hit -- (query, entry,
+ * score) with z-score >= z_min, same exact integer thresholds as sats_search_hits() -- to one device list from its arg-max
+ * epilogue (one atomicAdd per hit), query after query, pool after pool, while the search runs.  The dense Q x D score
+ * matrix never has to leave the device: sats_search_streamed_hits() copies back the hit count and the hits only
+ * (*d2h_bytes, may be NULL, receives the bytes it copied) and returns exactly what sats_search_hits(s, z_min, cap, ...)
+ * would (same rows, same device order); if the list overflowed (> 4 M hits) it falls back to that dense post-pass.
+ * z_min = NaN unbinds.  The cut stays bound across launches; every launch starts a fresh list.                    */
+int sats_search_bind_cut(sats_searcher *s, double z_min);
+int sats_search_streamed_hits(sats_searcher *s, int cap, int32_t *count_out, int32_t *index_out, int32_t *score_out,
+                              int64_t *d2h_bytes);
 int sats_searcher_sync(sats_searcher *s);
 /* kernels launched by this searcher since creation (for the bench's gpu_launches claim)          */
 long long sats_searcher_launch_count(const sats_searcher *s);
@@ -279,6 +289,9 @@ int sats_searcher_get_xorwow(sats_searcher *s, uint32_t *states6);
 int sats_searcher_reset_xorwow(sats_searcher *s, uint64_t seed);
 
 int sats_device_count(void);
+/* Create the device's CUDA context now.  Multi-GPU hosts: call it for every device from ONE thread before creating
+ * searchers from several (concurrent context creation is serialised by the driver and measurably slower).       */
+int sats_device_init(int device);
 
 /* ---- validation aids: the integer cut-offs the kernel compares raw 32-bit draws with ----------------------------------
  * Every decision the reference takes on a uniform u = curand_uniform-style unit(x) of 32 random bits x is monotone in x,

@@ -237,3 +237,30 @@ def test_device_significance_cut_matches_printed_z_scores(base, fixtures):
         assert len(got) == part.entries and (idx[q, part.entries:] == -1).all()
         assert sc[q, :len(got)].tolist() == full[q][got].tolist()
     part.close()
+
+
+def test_streamed_hits_equal_the_dense_post_pass(base, fixtures):
+    """SURVEY 8(f2), streaming form: with a cut bound, the kernels append their hits to a device list while they run;
+    reading that list must give exactly what sats_search_hits() selects from the dense scores afterwards -- per query,
+    same device order, same capacity rule -- while copying only the hits.  Multi-query batch, whole db and a shard,
+    cuts from 'nearly nothing' to 'everything'."""
+    db = base.bootstrap(6000, 21, True)
+    qs = as_db([fixtures["queries_by_name"][n] for n in ("D1UBIA_", "D2PHLB1", "d1twfa_")] + structures_of(db, [17, 5999]))
+    p = S.default_params(lorder=1, lsoln=0, restarts=64, seed=5)
+    for shard in ((0, 1), (2, 5)):
+        sr = S.Searcher(db, 0, *shard)
+        sr.upload(qs)
+        for z_min, cap in ((2.5, 6000), (1.0, 50), (-0.4, 6000), (-1e9, 6000)):
+            sr.bind_cut(z_min)
+            sr.launch(p)
+            cnt, idx, sc, nbytes = sr.streamed_hits(cap)
+            want = sr.hits(z_min, cap)
+            assert np.array_equal(cnt, want[0]) and np.array_equal(idx, want[1]) and np.array_equal(sc, want[2]), (shard, z_min)
+            assert nbytes == 4 + 16 * int(cnt.sum())                    # the counter and one 16-byte record per hit
+            if z_min >= 1.0:
+                assert nbytes < 0.05 * 4 * len(qs) * sr.entries           # a few per cent of the dense score matrix
+        sr.bind_cut(None)
+        sr.launch(p)
+        with pytest.raises(S.SatsError, match="bound cut"):
+            sr.streamed_hits(10)
+        sr.close()
