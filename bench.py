@@ -329,7 +329,10 @@ def ours(args):
             take[idx_host[valid]] = valid
             gathered = torch.empty(n_gpus * cap, dtype=torch.int32, device=dev)
             host = torch.empty(n_gpus * cap, dtype=torch.int32).pin_memory()
+        else:
+            gathered = torch.empty(n_gpus * cap, dtype=torch.int32, device=dev)
         pad = torch.zeros(cap, dtype=torch.int32, device=dev)
+        view = {}                        # device pointer of the searcher's score buffer -> torch view of it
 
         def step(timed_gather):
             sr.upload(qs)
@@ -337,8 +340,10 @@ def ours(args):
             sr.sync()
             g0 = time.perf_counter()
             ptr, _, n, _ = sr.device_results()
-            pad[:n].copy_(torch.as_tensor(_Dev(ptr, n), device=dev))
-            dist.gather(pad, list(gathered.view(n_gpus, cap).unbind(0)) if rank == 0 else None, dst=0)
+            if ptr not in view:
+                view[ptr] = torch.as_tensor(_Dev(ptr, n), device=dev)
+            pad[:n].copy_(view[ptr])
+            dist.all_gather_into_tensor(gathered, pad)          # one NCCL collective; every shard is ~4 B x D / N
             if rank == 0:
                 host.copy_(gathered, non_blocking=True)
                 torch.cuda.synchronize()
@@ -430,7 +435,7 @@ def ours(args):
                 "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_ms / args.steps,
                 "gather_ms_per_step": (gather_ms / args.steps) if n_gpus > 1 else None,
                 "path": "sats_search(): host query in, host scores out" if n_gpus == 1 else
-                        "per rank upload + launch; NCCL gather of the shards' device score vectors to rank 0; one D2H copy; "
+                        "per rank upload + launch; NCCL all-gather of the shards' device score vectors; one D2H copy on rank 0; "
                         "scatter by original index (gather_ms_per_step = that tail, rank 0)"},
         "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
         "reference_gpu_same_box": ref_gpu,

@@ -10,8 +10,11 @@
 #include <cstdio>
 #include <cstring>
 #include <numeric>
+#include <set>
 #include <thread>
 #include <vector>
+
+#include <time.h>
 
 #include <cuda_runtime.h>
 #include <curand_kernel.h>
@@ -26,6 +29,16 @@
       return sats_fail(SATS_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, \
                        cudaGetErrorString(e_));                                                          \
   } while (0)
+
+// SATS_TRACE=1: phase timings of searcher creation on stderr (diagnostics only)
+static double trace_now()
+{
+  timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return t.tv_sec * 1e3 + t.tv_nsec * 1e-6;
+}
+static const bool g_trace = getenv("SATS_TRACE") != nullptr;
+#define TRACE(what) do { if (g_trace) { double n_ = trace_now(); fprintf(stderr, "[sats dev %d] %-28s %9.2f ms\n", device, what, n_ - t_trace); t_trace = n_; } } while (0)
 
 static const int kScoreSentinel = (int)0x80808080;   // byte-memset pattern marking "not computed by this launch"
 static const int kMaxSmem = 227 * 1024;
@@ -170,7 +183,7 @@ struct sats_searcher {
   int4 *h_stream = nullptr; size_t h_stream_cap = 0;
   bool stream_valid = false;              // the last launch ran with the cut bound
   long long launches = 0;
-  bool attr_done = false;
+  std::set<kernel_fn> smem_opted;         // kernel variants already opted into 227 KB of dynamic shared memory
 };
 
 
@@ -237,6 +250,7 @@ try {
   if (!db || !out) return sats_fail(SATS_ERR_ARG, "sats_searcher_create: null argument");
   if (shard_count < 1) shard_count = 1;
   if (shard_rank < 0 || shard_rank >= shard_count) return sats_fail(SATS_ERR_ARG, "bad shard %d of %d", shard_rank, shard_count);
+  double t_trace = trace_now();
   int ndev = sats_device_count();
   if (ndev < 1) return sats_fail(SATS_ERR_CUDA, "no CUDA device available (this library has no CPU search path)");
   if (device < 0 || device >= ndev) return sats_fail(SATS_ERR_ARG, "device %d out of range (have %d)", device, ndev);
@@ -245,6 +259,7 @@ try {
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) return sats_fail(SATS_ERR_CUDA, "device %d is sm_%d%d; this build targets sm_100a", device, prop.major, prop.minor);
 
+  TRACE("set device + properties");
   sats_searcher *s = new sats_searcher();
   s->device = device;
   s->num_sms = prop.multiProcessorCount;
@@ -269,6 +284,7 @@ try {
     bytes[k] = (uint32_t)entry_blob_bytes(db->order[e]);
     total += bytes[k];
   }
+  TRACE("partition + sort");
   std::vector<uint8_t> blobs(total ? total : 16, 0);
   // the blobs are independent: fill them on a few host threads (100 k structures = 240 MB of cells)
   auto fill_range = [&](size_t k0, size_t k1) {
@@ -300,6 +316,7 @@ try {
     }
     for (auto &th : pool) th.join();
   }
+  TRACE("blob fill");
   auto fail = [&](int rc) { sats_searcher_free(s); return rc; };
 #define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(sats_fail(SATS_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_))); } while (0)
   CKF(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -310,12 +327,15 @@ try {
     CKF(cudaStreamCreateWithFlags(&s->side[i], cudaStreamNonBlocking));
     CKF(cudaEventCreateWithFlags(&s->side_done[i], cudaEventDisableTiming));
   }
+  TRACE("streams + events");
   CKF(cudaMalloc(&s->d_blobs, blobs.size()));
   CKF(cudaMalloc(&s->d_blob_off, std::max<size_t>(1, local.size()) * 8));
   CKF(cudaMalloc(&s->d_blob_bytes, std::max<size_t>(1, local.size()) * 4));
   CKF(cudaMalloc(&s->d_pool_list, std::max<size_t>(1, local.size()) * 4));
   CKF(cudaMalloc(&s->d_xw_blocks, SATS_REF_GRID_BLOCKS * 4));
+  TRACE("cudaMalloc x5");
   CKF(cudaMemcpy(s->d_blobs, blobs.data(), blobs.size(), cudaMemcpyHostToDevice));
+  TRACE("blob upload");
   CKF(cudaMalloc(&s->d_sorted_order, std::max<size_t>(1, local.size()) * 4));
   if (!local.empty()) {
     CKF(cudaMemcpy(s->d_blob_off, off.data(), local.size() * 8, cudaMemcpyHostToDevice));
@@ -334,6 +354,7 @@ try {
   CKF(cudaMemcpy(s->d_accept, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
   CKF(cudaMemcpy(s->d_accept + tab.size(), temps.data(), temps.size() * 4, cudaMemcpyHostToDevice));
   CKF(cudaMalloc(&s->d_xw, (size_t)SATS_REF_GRID_BLOCKS * SATS_REF_GRID_THREADS * 6 * 4));
+  TRACE("tables");
 #undef CKF
   *out = s;
   return SATS_OK;
@@ -490,17 +511,13 @@ static int ensure_results(sats_searcher *s, int qcount, int lsoln)
   return SATS_OK;
 }
 
-static int set_attrs_once(sats_searcher *s)
+// Opt the kernel variants this searcher actually launches into the full dynamic shared memory, once each (setting the
+// attribute on all 72 variants up front made the driver load every one of them: ~10 ms on a process's first search).
+static int allow_full_smem(sats_searcher *s, kernel_fn fn)
 {
-  if (s->attr_done) return SATS_OK;
-  const int ws[3] = {1, 2, 4};
-  for (int a = 0; a < 3; a++)
-    for (int b = 0; b < 3; b++)
-      for (int lo = 0; lo < 2; lo++)
-        for (int xw = 0; xw < 2; xw++)
-          for (int ls = 0; ls < 2; ls++)
-            CK(cudaFuncSetAttribute(pick_kernel(ws[a], ws[b], lo, xw, ls), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-  s->attr_done = true;
+  if (s->smem_opted.count(fn)) return SATS_OK;
+  CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  s->smem_opted.insert(fn);
   return SATS_OK;
 }
 
@@ -515,8 +532,7 @@ try {
   if (pp->accept_mode == SATS_ACCEPT_DEVICE_FAST && pp->rng_mode != SATS_RNG_XORWOW_GRID)
     return sats_fail(SATS_ERR_ARG, "ACCEPT_DEVICE_FAST exists for same-box parity with the reference GPU binary: use it with XORWOW_GRID");
   CK(cudaSetDevice(s->device));
-  int rc = set_attrs_once(s);
-  if (rc) return rc;
+  int rc = SATS_OK;
   const int D = (int)s->sorted_orig.size();
   const int Q = s->last_q;
   const bool xorwow = pp->rng_mode == SATS_RNG_XORWOW_GRID;
@@ -616,11 +632,13 @@ try {
         k.sm_query_bytes = qwords_for(n1) > 2 ? SATS_K_QUERY_HDR : (int)s->q_bytes[q];
         k.sm_mapwords = qwords_for(n1) > 2 ? (n1 + 3) / 4 : n1 + 2;      // word maps carry elements -1 and n1
         k.sm_bmapwords = pp->lsoln ? (n1 + 3) / 4 : 0;
-        k.sm_qmask_bytes = (int)round16((size_t)n1 * words_for(n2max) * 4);
+        k.sm_qmask_bytes = SATS_K_DSLOT_BYTES + (int)round16((size_t)n1 * words_for(n2max) * 4);
         k.sm_team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * k.tw * 4 + SATS_K_SCRATCH_BYTES + (size_t)(k.tw / 32) * k.sm_qmask_bytes);
         size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + SATS_K_ZTAB_BYTES + k.sm_team_bytes;
         if (smem > (size_t)kMaxSmem) return sats_fail(SATS_ERR_ARG, "query %d x entry order %d needs %zu B of shared memory", q, n2max, smem);
         kernel_fn fn = pick_kernel(qwords_for(n1), words_for(n2max), pp->lorder != 0, true, pp->lsoln != 0);
+        rc = allow_full_smem(s, fn);
+        if (rc) return rc;
         fn<<<dim3((unsigned)blocks.size(), 1), k.tw, smem, s->stream>>>(k);
         CK(cudaGetLastError());
         s->launches++;
@@ -649,49 +667,80 @@ try {
         k.sm_query_bytes = w1 > 2 ? SATS_K_QUERY_HDR : (int)qbmax;
         k.sm_mapwords = w1 > 2 ? (n1max + 3) / 4 : n1max + 2;      // word maps carry elements -1 and n1
         k.sm_bmapwords = pp->lsoln ? (n1max + 3) / 4 : 0;
-        int b0 = r0;
-        while (b0 < r1) {
-          // bucket = maximal run of entries whose order falls under the same bound (list is decreasing)
-          const int n2max = s->sorted_order[b0];
-          int lowbound = 0;
-          for (int bb : kBucketBounds) { if (bb >= n2max) break; lowbound = bb; }
-          int b1 = b0;
-          while (b1 < r1 && s->sorted_order[b1] > lowbound) b1++;
-          k.sm_entry_bytes = (int)entry_blob_bytes(n2max);
-              k.sm_qmask_bytes = (int)round16((size_t)n1max * words_for(n2max) * 4);
-          kernel_fn fn = pick_kernel(w1, words_for(n2max), pp->lorder != 0, false, pp->lsoln != 0);
-          // team width (threads sharing one entry; results do not depend on it) and teams per CTA: whatever keeps the
-          // most warps resident per SM; a narrower team only when it buys strictly more
-          int best_teams = 0, best_warps = -1, best_tw = 0, best_team_bytes = 0, best_ctas = 0;
-          // the choice depends only on the kernel variant and the shared-memory sizes: remember it (the occupancy queries
-          // below would otherwise cost a few hundred microseconds of host time per search)
+        // launch shape for a bucket whose largest entry has order n2max: team width (threads sharing one entry; results do
+        // not depend on it) and teams per CTA -- whatever keeps the most warps resident per SM, a narrower team only when
+        // it buys strictly more.  The choice depends only on the kernel variant and the shared-memory sizes: remember it (the
+        // occupancy queries would otherwise cost a few hundred microseconds of host time per search).
+        struct Shape { kernel_fn fn; int tw, teams, team_bytes, ctas, entry_bytes, qmask_bytes; };
+        auto shape_for = [&](int n2max, Shape *out) -> int {
+          Shape sh;
+          sh.entry_bytes = (int)entry_blob_bytes(n2max);
+          sh.qmask_bytes = SATS_K_DSLOT_BYTES + (int)round16((size_t)n1max * words_for(n2max) * 4);
+          sh.fn = pick_kernel(w1, words_for(n2max), pp->lorder != 0, false, pp->lsoln != 0);
+          int rc2 = allow_full_smem(s, sh.fn);
+          if (rc2) return rc2;
+          sh.tw = sh.teams = sh.team_bytes = sh.ctas = 0;
           const std::array<int, 8> cfg_key = {w1, words_for(n2max) * 4 + (pp->lorder != 0) * 2 + (pp->lsoln != 0), k.sm_query_bytes,
-                                              k.sm_entry_bytes, k.sm_mapwords, k.sm_bmapwords, tw_max * 64 + teams_cap, n1max};
+                                              sh.entry_bytes, k.sm_mapwords, k.sm_bmapwords, tw_max * 64 + teams_cap, n1max};
           auto hit = s->launch_cfg.find(cfg_key);
           if (hit != s->launch_cfg.end()) {
-            best_tw = hit->second[0]; best_teams = hit->second[1]; best_team_bytes = hit->second[2]; best_ctas = hit->second[3];
+            sh.tw = hit->second[0]; sh.teams = hit->second[1]; sh.team_bytes = hit->second[2]; sh.ctas = hit->second[3];
           } else {
+            int best_warps = -1;
             for (int tw = tw_max; tw >= 32; tw >>= 1) {
               if (tw & 31) continue;             // 96 -> 48: not a whole number of warps
-              const int team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * tw * 4 + SATS_K_SCRATCH_BYTES + (size_t)(tw / 32) * k.sm_qmask_bytes);
+              const int team_bytes = (int)round16(sh.entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * tw * 4 + SATS_K_SCRATCH_BYTES + (size_t)(tw / 32) * sh.qmask_bytes);
               const int teams_max = std::min(SATS_K_MAXTHREADS / tw, teams_cap);
               for (int teams = teams_max; teams >= 1; teams--) {
                 size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + SATS_K_ZTAB_BYTES + (size_t)teams * team_bytes;
                 if (smem > (size_t)kMaxSmem) continue;
                 int ctas = 0;
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, fn, teams * tw, smem));
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, sh.fn, teams * tw, smem));
                 if (ctas < 1) continue;            // does not fit at all
                 int warps = ctas * teams * tw / 32;
-                if (warps > best_warps) { best_warps = warps; best_teams = teams; best_tw = tw; best_team_bytes = team_bytes; best_ctas = ctas; }
+                if (warps > best_warps) { best_warps = warps; sh.teams = teams; sh.tw = tw; sh.team_bytes = team_bytes; sh.ctas = ctas; }
               }
             }
-            if (best_teams) s->launch_cfg[cfg_key] = {best_tw, best_teams, best_team_bytes, best_ctas};
+            if (sh.teams) s->launch_cfg[cfg_key] = {sh.tw, sh.teams, sh.team_bytes, sh.ctas};
           }
-          if (best_teams == 0) return sats_fail(SATS_ERR_ARG, "query order %d x entry order %d does not fit in shared memory", n1max, n2max);
-          const int tw = best_tw;
+          if (sh.teams == 0) return sats_fail(SATS_ERR_ARG, "query order %d x entry order %d does not fit in shared memory", n1max, n2max);
+          *out = sh;
+          return SATS_OK;
+        };
+        // end of the size class (kBucketBounds) that the entry at list position b belongs to (the list is decreasing)
+        auto class_end = [&](int b) {
+          int lowbound = 0;
+          for (int bb : kBucketBounds) { if (bb >= s->sorted_order[b]) break; lowbound = bb; }
+          int e = b;
+          while (e < r1 && s->sorted_order[e] > lowbound) e++;
+          return e;
+        };
+        static const bool no_merge = getenv("SATS_NO_MERGE") != nullptr;
+        int b0 = r0;
+        while (b0 < r1) {
+          // A bucket = one launch, its shared memory sized for its largest entry.  It starts as one size class and then
+          // absorbs the following (smaller) classes for as long as a launch of their own would not put more warps on an SM
+          // and they run the same kernel variant: one work queue over more entries balances the persistent teams better than
+          // several launches with a tail each -- which matters once a GPU holds only a 1/8 shard.
+          const int n2max = s->sorted_order[b0];
+          Shape sh;
+          rc = shape_for(n2max, &sh);
+          if (rc) return rc;
+          int b1 = class_end(b0);
+          while (!no_merge && b1 < r1 && words_for(s->sorted_order[b1]) == words_for(n2max)) {
+            Shape nx;
+            rc = shape_for(s->sorted_order[b1], &nx);
+            if (rc) return rc;
+            if (nx.ctas * nx.teams * nx.tw > sh.ctas * sh.teams * sh.tw) break;
+            b1 = class_end(b1);
+          }
+          kernel_fn fn = sh.fn;
+          k.sm_entry_bytes = sh.entry_bytes;
+          k.sm_qmask_bytes = sh.qmask_bytes;
+          const int tw = sh.tw, best_ctas = sh.ctas;
           k.tw = tw;
-          k.teams = best_teams;
-          k.sm_team_bytes = best_team_bytes;
+          k.teams = sh.teams;
+          k.sm_team_bytes = sh.team_bytes;
           k.item_first = b0; k.item_count = b1 - b0;
           size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + SATS_K_ZTAB_BYTES + (size_t)k.teams * k.sm_team_bytes;
           // persistent teams: no more CTAs than fit on the device at once (per query); each team keeps claiming entries

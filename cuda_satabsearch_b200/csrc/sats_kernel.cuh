@@ -292,6 +292,7 @@ struct TeamView {
   uint32_t ztab;           // the zeta table (128-byte aligned)
   const uint32_t *tmask;   // [4][4] type -> 128-bit mask of entry SSEs of that type
   uint32_t qmask;          // [n1][W2] per query SSE: the mask of entry SSEs of its type (built per entry, one load per move)
+  uint32_t dslot;          // this warp's 8 x 16 B of scratch for the cooperative deltasd (Chain::delta_flat)
   uint32_t smap;           // this lane's live map (Map<W1 <= 2>)
   uint32_t bmap;           // this lane's best map (Map<false>)
   uint32_t mstride;        // tw * 4: consecutive lanes own consecutive banks, so lane-private accesses never conflict
@@ -342,6 +343,11 @@ template <bool WIDE> struct Map {
 template <int W1, int W2, bool LORDER, bool XORWOW, bool LSOLN>
 struct Chain {
   typedef Map<(W1 <= 2)> LiveMap;
+#ifndef SATS_FLAT_DELTA
+#define SATS_FLAT_DELTA 0
+#endif
+  // cooperative deltasd (delta_flat below): for sparse maps, i.e. LORDER = T, and one-word query masks
+  static constexpr bool FLAT = SATS_FLAT_DELTA && LORDER && W1 == 1;
   uint32_t mq[W1];   // query SSEs currently mapped
   uint32_t md[W2];   // entry SSEs currently occupied
   int score;
@@ -475,11 +481,60 @@ struct Chain {
     return d;
   }
 
+  // deltasd for the whole warp at once.  With LORDER = T few lanes propose a state-changing move in any one step (~5 of 32,
+  // ~3 mapped partners each), so the per-lane walk above runs with 3-4 active lanes for as many rounds as the busiest lane has
+  // partners.  Here the lanes with a real move publish (partner mask, row addresses) in eight 16-byte slots of shared memory
+  // (slot = rank among the real lanes), every quad of lanes takes one slot and splits its partner mask by bit position
+  // modulo 4, the quad's partial sums meet in two shuffles, and the owner pulls its total from its quad's first lane.  More
+  // than eight real lanes take further passes.  Integer sums: the order of the terms does not matter, results are unchanged.
+  // Every lane of the warp must call this (ballot / shuffles with the full mask).
+  __device__ __forceinline__ int delta_flat(const TeamView &v, int lane, int i, int from, int to) const
+  {
+    const unsigned full = 0xffffffffu;
+    const bool real = (from >= 0) | (to >= 0);
+    const unsigned reals = __ballot_sync(full, real);
+    if (reals == 0u) return 0;
+    const int rank = __popc(reals & ((1u << lane) - 1u)), nreal = __popc(reals);
+    const uint32_t qrow = (v.qcell + (uint32_t)(i * v.n1) * 8u) | ((uint32_t)lane << 24);      // shared-window addresses are < 2^24
+    const uint32_t frow = v.ecell + (uint32_t)(from * v.n2) * 8u, trow = v.ecell + (uint32_t)(to * v.n2) * 8u;
+    const uint32_t cls = 0x11111111u << (lane & 3);
+    int d = 0;
+#pragma unroll 1
+    for (int base = 0; base < nreal; base += 8) {
+      const int slot = rank - base;
+      const bool mine = real && (unsigned)slot < 8u;
+      if (mine)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(v.dslot + (uint32_t)slot * 16u), "r"(mq[0] & ~(1u << i)),
+                     "r"(qrow), "r"(frow), "r"(trow) : "memory");
+      __syncwarp();
+      uint32_t b = 0u, oq = 0u, of = 0u, ot = 0u;
+      if (base + (lane >> 2) < nreal)
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(b), "=r"(oq), "=r"(of), "=r"(ot) : "r"(v.dslot + (uint32_t)(lane >> 2) * 16u) : "memory");
+      b &= cls;
+      const uint32_t omap = v.smap + (uint32_t)(((int)(oq >> 24) - lane) * 4);      // the owner's lane-private map
+      oq &= 0xffffffu;
+      int part = 0;
+      while (b) {
+        const int z = top_bit(b);
+        b &= bits_below(z);
+        const uint32_t l8 = LiveMap::off8(omap, z, v.mstride);
+        const uint2 q = lds64(oq + (uint32_t)z * 8u);
+        const uint2 ef = lds64(of + l8), et = lds64(ot + l8);
+        part += gated(q, et) - gated(q, ef);
+      }
+      part += __shfl_xor_sync(full, part, 1);
+      part += __shfl_xor_sync(full, part, 2);
+      const int got = __shfl_sync(full, part, (slot & 7) << 2);
+      if (mine) d = got;
+    }
+    return d;
+  }
+
   // One Metropolis move (kernel.cu:1032-1191) on query SSE i = pick_index(first draw of the move).  u2/u3 are callables
   // returning 32 random bits, so that a sequential generator is advanced exactly when the reference would draw (u2 only
   // with >= 2 candidates).
   template <class U2, class U3>
-  __device__ __forceinline__ void move(const TeamView &v, int m, const SatsKParams &p, int &best, int &best_tag, int tag,
+  __device__ __forceinline__ void move(const TeamView &v, int m, const SatsKParams &p, int &best, int &best_tag, int tag, int lane,
                                        const int i, U2 &&u2, U3 &&u3)
   {
     const bool was_mapped = bit_test<W1>(mq, i);
@@ -518,7 +573,8 @@ struct Chain {
     else if (ncand > 1) to = select_nth<W2>(cand, scaled_index(unit_from_bits(u2()), ncand));
 
     int d = 0;
-    if (from >= 0 || to >= 0) d = delta(v, i, from, to);
+    if (FLAT) d = delta_flat(v, lane, i, from, to);
+    else if (from >= 0 || to >= 0) d = delta(v, i, from, to);
     const int cand_score = score + d;
     const bool improved = cand_score > best;
     if (improved) {
@@ -586,8 +642,14 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
   int best_tag = tl;                                  // XORWOW: thread id; Philox: restart index of the best chain
   const int chains = XORWOW ? ((p.restarts + p.tw - 1) / p.tw) * p.tw : p.restarts;
 
-  for (int r = tl; r < chains; r += p.tw) {
+  // The cooperative deltasd needs whole warps: a warp runs while ANY of its lanes has a restart left, the lanes beyond the
+  // last restart run a ghost chain (streams nobody else uses) whose results are discarded.
+  typedef Chain<W1, W2, LORDER, XORWOW, LSOLN> ChainT;
+  for (int r = tl; (ChainT::FLAT ? (r & ~31) : r) < chains; r += p.tw) {
     const int tag = XORWOW ? tl : r;
+    const bool ghost = ChainT::FLAT && r >= chains;
+    const int best_so_far = best;
+    if (ghost) best = 0x3fffffff;                      // nothing a ghost finds can improve on this
     if (XORWOW) {
       ch.seed(v, [&](int) { return xw.next() < p.seed_cut; });
     } else {
@@ -605,7 +667,7 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
     }
     if (XORWOW) {
       for (int m = 0; m < SATS_K_MOVES; m++)
-        ch.move(v, m, p, best, best_tag, tag, pick_index(xw.next(), v.n1, v.pick_cut), [&] { return xw.next(); }, [&] { return xw.next(); });
+        ch.move(v, m, p, best, best_tag, tag, tl & 31, pick_index(xw.next(), v.n1, v.pick_cut), [&] { return xw.next(); }, [&] { return xw.next(); });
     } else {
       // static draw positions: Philox block g feeds moves 2g (words 0, 1) and 2g + 1 (words 2, 3); per move the first word
       // picks the SSE (and, hashed, the candidate), the second is the Metropolis draw
@@ -617,13 +679,14 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
         // the SSE picks depend on the draws only, not on the chains' state: issued together, off the moves' critical path
         const int i0 = pick_index(a[0], v.n1, v.pick_cut), i1 = pick_index(a[2], v.n1, v.pick_cut);
         const int i2 = pick_index(b[0], v.n1, v.pick_cut), i3 = pick_index(b[2], v.n1, v.pick_cut);
-        ch.move(v, m + 0, p, best, best_tag, tag, i0, [&] { return candidate_bits(a[0]); }, [&] { return a[1]; });
-        ch.move(v, m + 1, p, best, best_tag, tag, i1, [&] { return candidate_bits(a[2]); }, [&] { return a[3]; });
-        ch.move(v, m + 2, p, best, best_tag, tag, i2, [&] { return candidate_bits(b[0]); }, [&] { return b[1]; });
-        ch.move(v, m + 3, p, best, best_tag, tag, i3, [&] { return candidate_bits(b[2]); }, [&] { return b[3]; });
+        ch.move(v, m + 0, p, best, best_tag, tag, tl & 31, i0, [&] { return candidate_bits(a[0]); }, [&] { return a[1]; });
+        ch.move(v, m + 1, p, best, best_tag, tag, tl & 31, i1, [&] { return candidate_bits(a[2]); }, [&] { return a[3]; });
+        ch.move(v, m + 2, p, best, best_tag, tag, tl & 31, i2, [&] { return candidate_bits(b[0]); }, [&] { return b[1]; });
+        ch.move(v, m + 3, p, best, best_tag, tag, tl & 31, i3, [&] { return candidate_bits(b[2]); }, [&] { return b[3]; });
       }
     }
     if (LSOLN) ch.finish_best_map(v);
+    if (ghost) best = best_so_far;
   }
 
   // ---- arg-max over the team: highest score, lowest tag (kernel.cu:1205-1221 scans thread 0..127 with '>')
@@ -701,7 +764,8 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
   v.bmap = smem_u32(bmaps + tl * 4);
   // team scratch: red[2][4] (two alternating arg-max buffers) | claim[2] | per-warp qmask copies
   volatile int *claim = reinterpret_cast<volatile int *>(red + 8);
-  v.qmask = smem_u32(reinterpret_cast<uint8_t *>(red) + SATS_K_SCRATCH_BYTES + (tl >> 5) * p.sm_qmask_bytes);
+  v.dslot = smem_u32(reinterpret_cast<uint8_t *>(red) + SATS_K_SCRATCH_BYTES + (tl >> 5) * p.sm_qmask_bytes);     // per warp: slots, then qmask
+  v.qmask = v.dslot + SATS_K_DSLOT_BYTES;
   Xorwow xw;
 
   if (!XORWOW) {
