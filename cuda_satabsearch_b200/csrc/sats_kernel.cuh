@@ -37,6 +37,10 @@
 #include "sats.h"
 #include "sats_kparams.h"
 
+#ifndef SATS_SPLIT_LAYOUT
+#define SATS_SPLIT_LAYOUT 1
+#endif
+
 namespace satsk {
 
 // ------------------------------------------------------------------------------------------------ PTX
@@ -288,7 +292,9 @@ struct TeamView {
   uint32_t qcell;          // n1 x n1 {distance bits, code} (W1 <= 2)
   const uint8_t *qtype;    // n1
   uint32_t pick_cut;       // n1 words: exact boundaries of the SSE pick (pick_index)
-  uint32_t ecell;          // n2 x n2, preceded by "row -1": n2 cells of NaN distance (the missing side of a move)
+  uint32_t ecell;          // row 0 of the entry matrix; right in front of it "row -1": NaN distances (the missing side of a move)
+  uint32_t erow;           // split layout: bytes per row of the entry matrix, 4 n2 + round4(n2)
+  uint32_t ecode;          // split layout: offset of a row's code bytes behind its distances (4 n2)
   uint32_t ztab;           // the zeta table (128-byte aligned)
   const uint32_t *tmask;   // [4][4] type -> 128-bit mask of entry SSEs of that type
   uint32_t qmask;          // [n1][W2] per query SSE: the mask of entry SSEs of its type (built per entry, one load per move)
@@ -301,35 +307,36 @@ struct TeamView {
 
 // Lane-private maps (query SSE -> partner entry SSE) in two representations, both laid out so that consecutive lanes own
 // consecutive banks (stride = tw * 4 bytes between a lane's successive words):
-//   Map<true>   one 32-bit word per query SSE holding 8 * partner (-8 = unmapped): one IMAD to address, and the value is
-//               already the byte offset of the partner's cell in a row.  Used for the live map of queries of <= 64 SSEs.
+//   Map<true>   one 32-bit word per query SSE holding partner << LOG (unmapped = -1 << LOG): one IMAD to address, and the
+//               value is already the byte offset of the partner's cell in a row (LOG = 3: 8-byte {distance, code} cells;
+//               LOG = 2: the split layout's 4-byte distances).  Used for the live map of queries of <= 64 SSEs.
 //   Map<false>  one byte per query SSE (0xff = unmapped), four to a word.  A quarter of the shared memory, three more
 //               instructions per access: used for the live map of larger queries and for every best-so-far map.
-template <bool WIDE> struct Map {
+template <bool WIDE, int LOG = 3> struct Map {
   static __device__ __forceinline__ uint32_t addr(uint32_t base, int k, uint32_t stride)
   {
     if (WIDE) return base + (uint32_t)k * stride;
     return (uint32_t)(k >> 2) * stride + (base | (uint32_t)(k & 3));      // the lane's slot is 4-byte aligned
   }
-  // 8 * partner of a MAPPED query SSE
+  // partner << LOG of a MAPPED query SSE: the byte offset of the partner's cell within a row of the entry matrix
   static __device__ __forceinline__ uint32_t off8(uint32_t base, int k, uint32_t stride)
   {
     uint32_t v;
     if (WIDE) asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory");
-    else { asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory"); v <<= 3; }
+    else { asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory"); v <<= LOG; }
     return v;
   }
   // partner of a query SSE, -1 if unmapped
   static __device__ __forceinline__ int get(uint32_t base, int k, uint32_t stride)
   {
     int v;
-    if (WIDE) { asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory"); return v >> 3; }
+    if (WIDE) { asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory"); return v >> LOG; }
     asm("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory");
     return v;
   }
   static __device__ __forceinline__ void put(uint32_t base, int k, uint32_t stride, int j)      // j = -1 unmaps
   {
-    if (WIDE) asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr(base, k, stride)), "r"(j * 8) : "memory");
+    if (WIDE) asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr(base, k, stride)), "r"(j * (1 << LOG)) : "memory");
     else asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr(base, k, stride)), "r"(j) : "memory");
   }
   static __device__ __forceinline__ int words(int n1) { return WIDE ? n1 : (n1 + 3) >> 2; }
@@ -337,12 +344,31 @@ template <bool WIDE> struct Map {
   {
 #pragma unroll 1
     for (int w = 0; w < words(n1); w++)
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (uint32_t)w * stride), "r"(WIDE ? -8 : -1) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (uint32_t)w * stride), "r"(WIDE ? -(1 << LOG) : -1) : "memory");
   }
 };
 template <int W1, int W2, bool LORDER, bool XORWOW, bool LSOLN>
 struct Chain {
-  typedef Map<(W1 <= 2)> LiveMap;
+  // Entries of more than 32 SSEs (W2 >= 2) come to the production kernels in the SPLIT layout -- per row n2 fp32 distances,
+  // then n2 one-byte codes: 5 instead of 8 bytes per cell, so that more teams' entries fit an SM (these launches are
+  // occupancy-bound by shared memory) -- at the price of two loads per operand.  The validation kernels walk pools of mixed
+  // sizes and always read the 8-byte cells.
+  static constexpr bool SPLIT = SATS_SPLIT_LAYOUT && W2 >= 2 && !XORWOW;
+  typedef Map<(W1 <= 2), (SPLIT ? 2 : 3)> LiveMap;
+  // address of row j of the entry matrix (j = -1: the NaN row)
+  static __device__ __forceinline__ uint32_t entry_row(const TeamView &v, int j)
+  {
+    return SPLIT ? v.ecell + (uint32_t)j * v.erow : v.ecell + (uint32_t)(j * v.n2) * 8u;
+  }
+  // the entry cell in row `row` (a shared-window address) at the column whose byte offset is `off` (LiveMap::off8)
+  static __device__ __forceinline__ uint2 entry_cell(const TeamView &v, uint32_t row, uint32_t off)
+  {
+    if (!SPLIT) return lds64(row + off);
+    uint2 c;
+    c.x = lds32(row + off);
+    asm("ld.shared.u8 %0, [%1];" : "=r"(c.y) : "r"(row + v.ecode + (off >> 2)) : "memory");
+    return c;
+  }
 #ifndef SATS_FLAT_DELTA
 #define SATS_FLAT_DELTA 0
 #endif
@@ -433,7 +459,7 @@ struct Chain {
       while (bi) {
         int i = 32 * wi + __ffs(bi) - 1;
         bi &= bi - 1u;
-        const uint32_t erow = v.ecell + LiveMap::off8(v.smap, i, v.mstride) * (uint32_t)v.n2;
+        const uint32_t erow = SPLIT ? entry_row(v, LiveMap::get(v.smap, i, v.mstride)) : v.ecell + LiveMap::off8(v.smap, i, v.mstride) * (uint32_t)v.n2;
         const uint32_t qrow = v.qcell + (uint32_t)(i * v.n1) * 8u;
         const uint2 *qrow_g = v.qcell_g + i * v.n1;
 #pragma unroll
@@ -445,7 +471,7 @@ struct Chain {
             int k = 32 * wk + __ffs(bk) - 1;
             bk &= bk - 1u;
             total += gated(W1 > 2 ? with_table<true>(__ldg(qrow_g + k), v.ztab) : lds64(qrow + (uint32_t)k * 8u),
-                           lds64(erow + LiveMap::off8(v.smap, k, v.mstride)));
+                           entry_cell(v, erow, LiveMap::off8(v.smap, k, v.mstride)));
           }
         }
       }
@@ -461,8 +487,8 @@ struct Chain {
     int d = 0;
     const uint2 *qrow_g = v.qcell_g + i * v.n1;                         // W1 == 4: query cells live in global memory
     uint32_t qrow = W1 > 2 ? 0u : v.qcell + (uint32_t)(i * v.n1) * 8u;  // row base addresses, hoisted by hand
-    uint32_t frow = v.ecell + (uint32_t)(from * v.n2) * 8u;         // from / to = -1: the NaN row in front of the matrix
-    uint32_t trow = v.ecell + (uint32_t)(to * v.n2) * 8u;
+    uint32_t frow = entry_row(v, from);         // from / to = -1: the NaN row in front of the matrix
+    uint32_t trow = entry_row(v, to);
     asm volatile("" : "+r"(qrow), "+r"(frow), "+r"(trow));       // keep the compiler from re-folding them into the loop
 #pragma unroll
     for (int w = 0; w < W1; w++) {
@@ -474,7 +500,7 @@ struct Chain {
         const int k = 32 * w + z;
         const uint32_t l8 = LiveMap::off8(v.smap, k, v.mstride);
         const uint2 q = W1 > 2 ? with_table<true>(__ldg(qrow_g + k), v.ztab) : lds64(qrow + (uint32_t)k * 8u);
-        const uint2 ef = lds64(frow + l8), et = lds64(trow + l8);
+        const uint2 ef = entry_cell(v, frow, l8), et = entry_cell(v, trow, l8);
         d += gated(q, et) - gated(q, ef);
       }
     }
@@ -496,7 +522,7 @@ struct Chain {
     if (reals == 0u) return 0;
     const int rank = __popc(reals & ((1u << lane) - 1u)), nreal = __popc(reals);
     const uint32_t qrow = (v.qcell + (uint32_t)(i * v.n1) * 8u) | ((uint32_t)lane << 24);      // shared-window addresses are < 2^24
-    const uint32_t frow = v.ecell + (uint32_t)(from * v.n2) * 8u, trow = v.ecell + (uint32_t)(to * v.n2) * 8u;
+    const uint32_t frow = entry_row(v, from), trow = entry_row(v, to);
     const uint32_t cls = 0x11111111u << (lane & 3);
     int d = 0;
 #pragma unroll 1
@@ -519,7 +545,7 @@ struct Chain {
         b &= bits_below(z);
         const uint32_t l8 = LiveMap::off8(omap, z, v.mstride);
         const uint2 q = lds64(oq + (uint32_t)z * 8u);
-        const uint2 ef = lds64(of + l8), et = lds64(ot + l8);
+        const uint2 ef = entry_cell(v, of, l8), et = entry_cell(v, ot, l8);
         part += gated(q, et) - gated(q, ef);
       }
       part += __shfl_xor_sync(full, part, 1);
@@ -633,8 +659,8 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
     for (int w = 0; w < W2; w++) asm volatile("st.shared.b32 [%0], %1;" ::"r"(v.qmask + (uint32_t)(k * W2 + w) * 4u), "r"(tm[w]) : "memory");
   }
   if (W1 <= 2) {                                                   // see Chain::move: the window bounds of "nothing mapped below / above"
-    Map<true>::put(v.smap, -1, v.mstride, v.n2);
-    Map<true>::put(v.smap, v.n1, v.mstride, -1);
+    Chain<W1, W2, LORDER, XORWOW, LSOLN>::LiveMap::put(v.smap, -1, v.mstride, v.n2);
+    Chain<W1, W2, LORDER, XORWOW, LSOLN>::LiveMap::put(v.smap, v.n1, v.mstride, -1);
   }
   __syncwarp();
   Chain<W1, W2, LORDER, XORWOW, LSOLN> ch;
@@ -794,9 +820,10 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
     auto fetch = [&](int idx) {
       if (idx < p.item_count) {
         const int e = p.item_first + idx;
-        const uint32_t bytes = p.blob_bytes[e];
+        const bool split = Chain<W1, W2, LORDER, false, LSOLN>::SPLIT;
+        const uint32_t bytes = split ? p.blob_bytes_split[e] : p.blob_bytes[e];
         mbar_expect_tx(tbar, bytes);
-        tma_load_1d(se, p.blobs + p.blob_off[e], bytes, tbar);
+        tma_load_1d(se, p.blobs + (split ? p.blob_off_split[e] : p.blob_off[e]), bytes, tbar);
       }
     };
     if (tl == 0) fetch(claim_next(0));
@@ -811,7 +838,13 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
       mbar_wait(tbar, phase);
       phase ^= 1u;
       v.n2 = eh[0];
-      v.ecell = ecell0 + 8u * (uint32_t)v.n2;
+      if (Chain<W1, W2, LORDER, false, LSOLN>::SPLIT) {
+        v.ecode = 4u * (uint32_t)v.n2;
+        v.erow = v.ecode + (((uint32_t)v.n2 + 3u) & ~3u);
+        v.ecell = ecell0 + v.erow;
+      } else {
+        v.ecell = ecell0 + 8u * (uint32_t)v.n2;
+      }
       anneal_entry<W1, W2, LORDER, false, LSOLN>(p, v, team, tl, red + 4 * par, (uint32_t)eh[1], p.q_index_base + (uint32_t)qh[1], xw, qi, p.item_first + idx,
                                                  [&] { if (tl == 0) claim_next(par ^ 1); },
                                                  [&] { if (tl == 0) fetch(claim[par ^ 1]); });

@@ -23,6 +23,8 @@ struct SatsKParams {
   const uint8_t *blobs;            // entry blobs, each 16-byte aligned
   const uint64_t *blob_off;        // byte offset of entry k
   const uint32_t *blob_bytes;      // size of entry k's blob (multiple of 16)
+  const uint64_t *blob_off_split;  // the same for the split layout (entries of more than 32 SSEs have a second blob: per row n2 fp32
+  const uint32_t *blob_bytes_split;//   distances, then n2 code bytes); entries of <= 32 SSEs point at their one and only blob
   // queries of this launch: blockIdx.y selects one
   const uint8_t *qblobs;
   const uint64_t *qblob_off;
