@@ -391,11 +391,7 @@ def ours(args):
     if pj.exists():
         prof = json.loads(pj.read_text())
     orders = db.orders().astype(np.int64)
-    # every entry blob is read once per query: 8-byte {distance, code} cells up to 32 SSEs, the split layout (per row n2 fp32
-    # distances + n2 code bytes) above
-    cells8 = (80 + 8 * orders * (orders + 1) + 15) // 16 * 16
-    split = (80 + (4 * orders + (orders + 3) // 4 * 4) * (orders + 1) + 15) // 16 * 16
-    blob_bytes = float(np.where(orders > 32, split, cells8).sum())
+    blob_bytes = float(((80 + 8 * orders * (orders + 1) + 15) // 16 * 16).sum())      # every entry blob is read once per query
     roofline = {
         "bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
         "traffic": prof.get("dram_bytes_per_step"),

@@ -138,8 +138,8 @@ struct sats_searcher {
   std::vector<int32_t> sorted_order;
   std::vector<int32_t> file_rank;         // local sorted position -> rank in original file order among local entries
   uint8_t *d_blobs = nullptr;
-  uint64_t *d_blob_off = nullptr, *d_blob_off_split = nullptr;
-  uint32_t *d_blob_bytes = nullptr, *d_blob_bytes_split = nullptr;
+  uint64_t *d_blob_off = nullptr;
+  uint32_t *d_blob_bytes = nullptr;
   uint32_t *d_accept = nullptr;          // Metropolis cut-offs [moves][230], then the fp32 temperature schedule [moves]
   uint32_t accept_cut0 = 0, seed_cut = 0;
   uint32_t *d_xw = nullptr;
@@ -208,14 +208,6 @@ static int query_class(int n)
 }
 static size_t round16(size_t x) { return (x + 15) & ~(size_t)15; }
 static size_t entry_blob_bytes(int n) { return round16(SATS_K_ENTRY_HDR + 8 * (size_t)n * (n + 1)); }     // header, NaN row, n x n cells
-// split layout (entries of more than 32 SSEs, production kernels): header, then rows -1 .. n-1 of n fp32 distances + n code bytes
-static size_t split_row_bytes(int n) { return 4 * (size_t)n + (((size_t)n + 3) & ~(size_t)3); }
-static size_t split_blob_bytes(int n) { return round16(SATS_K_ENTRY_HDR + split_row_bytes(n) * (size_t)(n + 1)); }
-#ifndef SATS_SPLIT_LAYOUT
-#define SATS_SPLIT_LAYOUT 1
-#endif
-static const bool kSplitLayout = SATS_SPLIT_LAYOUT != 0;
-static const int kSplitAbove = 32;      // = the largest order a one-word entry mask (W2 = 1) covers
 static size_t query_blob_bytes(int n) { return round16(SATS_K_QUERY_HDR + 8 * (size_t)n * n); }
 
 static void fill_cells(const sats_db *db, int e, uint8_t *cells)
@@ -292,16 +284,6 @@ try {
     bytes[k] = (uint32_t)entry_blob_bytes(db->order[e]);
     total += bytes[k];
   }
-  // entries of more than 32 SSEs get a second blob in the split layout, behind all the 8-byte-cell blobs
-  std::vector<uint64_t> off_split(off);
-  std::vector<uint32_t> bytes_split(bytes);
-  for (size_t k = 0; k < local.size(); k++) {
-    const int n = s->sorted_order[k];
-    if (n <= kSplitAbove) continue;
-    off_split[k] = total;
-    bytes_split[k] = (uint32_t)split_blob_bytes(n);
-    total += bytes_split[k];
-  }
   TRACE("partition + sort");
   std::vector<uint8_t> blobs(total ? total : 16, 0);
   // the blobs are independent: fill them on a few host threads (100 k structures = 240 MB of cells)
@@ -318,20 +300,6 @@ try {
     // addresses a row whose gate never opens without any special casing in the kernel
     for (int j = 0; j < n; j++) { const uint32_t nan_cell[2] = {0x7fc00000u, 0u}; memcpy(b + SATS_K_ENTRY_HDR + 8 * (size_t)j, nan_cell, 8); }
     fill_cells(db, e, b + SATS_K_ENTRY_HDR + 8 * (size_t)n);
-    if (n > kSplitAbove) {
-      uint8_t *b2 = blobs.data() + off_split[k];
-      memcpy(b2, b, SATS_K_ENTRY_HDR);
-      const size_t rb = split_row_bytes(n);
-      for (int i = -1; i < n; i++) {
-        uint8_t *row = b2 + SATS_K_ENTRY_HDR + rb * (size_t)(i + 1);
-        for (int j = 0; j < n; j++) {
-          const float d = i < 0 ? std::nanf("") : db->dist(e, i, j);
-          const uint32_t raw = i < 0 ? 0u : db->code(e, i, j);
-          memcpy(row + 4 * (size_t)j, &d, 4);
-          row[4 * (size_t)n + (size_t)j] = (uint8_t)((std::min(raw >> 4, 4u) << 4) | std::min(raw & 15u, 4u));
-        }
-      }
-    }
   }
   };
   {
@@ -363,8 +331,6 @@ try {
   CKF(cudaMalloc(&s->d_blobs, blobs.size()));
   CKF(cudaMalloc(&s->d_blob_off, std::max<size_t>(1, local.size()) * 8));
   CKF(cudaMalloc(&s->d_blob_bytes, std::max<size_t>(1, local.size()) * 4));
-  CKF(cudaMalloc(&s->d_blob_off_split, std::max<size_t>(1, local.size()) * 8));
-  CKF(cudaMalloc(&s->d_blob_bytes_split, std::max<size_t>(1, local.size()) * 4));
   CKF(cudaMalloc(&s->d_pool_list, std::max<size_t>(1, local.size()) * 4));
   CKF(cudaMalloc(&s->d_xw_blocks, SATS_REF_GRID_BLOCKS * 4));
   TRACE("cudaMalloc x5");
@@ -374,8 +340,6 @@ try {
   if (!local.empty()) {
     CKF(cudaMemcpy(s->d_blob_off, off.data(), local.size() * 8, cudaMemcpyHostToDevice));
     CKF(cudaMemcpy(s->d_blob_bytes, bytes.data(), local.size() * 4, cudaMemcpyHostToDevice));
-    CKF(cudaMemcpy(s->d_blob_off_split, off_split.data(), local.size() * 8, cudaMemcpyHostToDevice));
-    CKF(cudaMemcpy(s->d_blob_bytes_split, bytes_split.data(), local.size() * 4, cudaMemcpyHostToDevice));
     CKF(cudaMemcpy(s->d_sorted_order, s->sorted_order.data(), local.size() * 4, cudaMemcpyHostToDevice));
   }
   // Metropolis cut-offs and temperatures exactly as the reference's host path evaluates them
@@ -402,7 +366,7 @@ extern "C" void sats_searcher_free(sats_searcher *s)
   if (!s) return;
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
-  cudaFree(s->d_blobs); cudaFree(s->d_blob_off); cudaFree(s->d_blob_bytes); cudaFree(s->d_blob_off_split); cudaFree(s->d_blob_bytes_split); cudaFree(s->d_accept); cudaFree(s->d_xw);
+  cudaFree(s->d_blobs); cudaFree(s->d_blob_off); cudaFree(s->d_blob_bytes); cudaFree(s->d_accept); cudaFree(s->d_xw);
   cudaFree(s->d_pool_list); cudaFree(s->d_xw_blocks); cudaFree(s->d_counters); cudaFree(s->d_qblobs); cudaFree(s->d_qoff); cudaFree(s->d_qbytes);
   cudaFree(s->d_scores); cudaFree(s->d_maps); cudaFree(s->d_topk); cudaFreeHost(s->h_topk);
   cudaFree(s->d_sorted_order); cudaFree(s->d_hits); cudaFreeHost(s->h_hits);
@@ -619,7 +583,6 @@ try {
   SatsKParams k;
   memset(&k, 0, sizeof k);
   k.blobs = s->d_blobs; k.blob_off = s->d_blob_off; k.blob_bytes = s->d_blob_bytes;
-  k.blob_off_split = s->d_blob_off_split; k.blob_bytes_split = s->d_blob_bytes_split;
   k.qblobs = s->d_qblobs; k.qblob_off = s->d_qoff; k.qblob_bytes = s->d_qbytes;
   k.restarts = pp->restarts; k.lsoln = pp->lsoln; k.accept_mode = pp->accept_mode;
   for (uint32_t r = 0; r < 10; r++) {
@@ -669,7 +632,7 @@ try {
         k.sm_query_bytes = qwords_for(n1) > 2 ? SATS_K_QUERY_HDR : (int)s->q_bytes[q];
         k.sm_mapwords = qwords_for(n1) > 2 ? (n1 + 3) / 4 : n1 + 2;      // word maps carry elements -1 and n1
         k.sm_bmapwords = pp->lsoln ? (n1 + 3) / 4 : 0;
-        k.sm_qmask_bytes = SATS_K_DSLOT_BYTES + (int)round16((size_t)n1 * words_for(n2max) * 4);
+        k.sm_qmask_bytes = (int)round16((size_t)n1 * words_for(n2max) * 4);
         k.sm_team_bytes = (int)round16(k.sm_entry_bytes + (size_t)(k.sm_mapwords + k.sm_bmapwords) * k.tw * 4 + SATS_K_SCRATCH_BYTES + (size_t)(k.tw / 32) * k.sm_qmask_bytes);
         size_t smem = SATS_K_BAR_BYTES + k.sm_query_bytes + SATS_K_ZTAB_BYTES + k.sm_team_bytes;
         if (smem > (size_t)kMaxSmem) return sats_fail(SATS_ERR_ARG, "query %d x entry order %d needs %zu B of shared memory", q, n2max, smem);
@@ -711,8 +674,8 @@ try {
         struct Shape { kernel_fn fn; int tw, teams, team_bytes, ctas, entry_bytes, qmask_bytes; };
         auto shape_for = [&](int n2max, Shape *out) -> int {
           Shape sh;
-          sh.entry_bytes = (int)(kSplitLayout && n2max > kSplitAbove ? split_blob_bytes(n2max) : entry_blob_bytes(n2max));
-          sh.qmask_bytes = SATS_K_DSLOT_BYTES + (int)round16((size_t)n1max * words_for(n2max) * 4);
+          sh.entry_bytes = (int)entry_blob_bytes(n2max);
+          sh.qmask_bytes = (int)round16((size_t)n1max * words_for(n2max) * 4);
           sh.fn = pick_kernel(w1, words_for(n2max), pp->lorder != 0, false, pp->lsoln != 0);
           int rc2 = allow_full_smem(s, sh.fn);
           if (rc2) return rc2;

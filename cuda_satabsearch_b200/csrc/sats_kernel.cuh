@@ -37,10 +37,6 @@
 #include "sats.h"
 #include "sats_kparams.h"
 
-#ifndef SATS_SPLIT_LAYOUT
-#define SATS_SPLIT_LAYOUT 1
-#endif
-
 namespace satsk {
 
 // ------------------------------------------------------------------------------------------------ PTX
@@ -292,13 +288,10 @@ struct TeamView {
   uint32_t qcell;          // n1 x n1 {distance bits, code} (W1 <= 2)
   const uint8_t *qtype;    // n1
   uint32_t pick_cut;       // n1 words: exact boundaries of the SSE pick (pick_index)
-  uint32_t ecell;          // row 0 of the entry matrix; right in front of it "row -1": NaN distances (the missing side of a move)
-  uint32_t erow;           // split layout: bytes per row of the entry matrix, 4 n2 + round4(n2)
-  uint32_t ecode;          // split layout: offset of a row's code bytes behind its distances (4 n2)
+  uint32_t ecell;          // n2 x n2, preceded by "row -1": n2 cells of NaN distance (the missing side of a move)
   uint32_t ztab;           // the zeta table (128-byte aligned)
   const uint32_t *tmask;   // [4][4] type -> 128-bit mask of entry SSEs of that type
   uint32_t qmask;          // [n1][W2] per query SSE: the mask of entry SSEs of its type (built per entry, one load per move)
-  uint32_t dslot;          // this warp's 8 x 16 B of scratch for the cooperative deltasd (Chain::delta_flat)
   uint32_t smap;           // this lane's live map (Map<W1 <= 2>)
   uint32_t bmap;           // this lane's best map (Map<false>)
   uint32_t mstride;        // tw * 4: consecutive lanes own consecutive banks, so lane-private accesses never conflict
@@ -307,36 +300,35 @@ struct TeamView {
 
 // Lane-private maps (query SSE -> partner entry SSE) in two representations, both laid out so that consecutive lanes own
 // consecutive banks (stride = tw * 4 bytes between a lane's successive words):
-//   Map<true>   one 32-bit word per query SSE holding partner << LOG (unmapped = -1 << LOG): one IMAD to address, and the
-//               value is already the byte offset of the partner's cell in a row (LOG = 3: 8-byte {distance, code} cells;
-//               LOG = 2: the split layout's 4-byte distances).  Used for the live map of queries of <= 64 SSEs.
+//   Map<true>   one 32-bit word per query SSE holding 8 * partner (-8 = unmapped): one IMAD to address, and the value is
+//               already the byte offset of the partner's cell in a row.  Used for the live map of queries of <= 64 SSEs.
 //   Map<false>  one byte per query SSE (0xff = unmapped), four to a word.  A quarter of the shared memory, three more
 //               instructions per access: used for the live map of larger queries and for every best-so-far map.
-template <bool WIDE, int LOG = 3> struct Map {
+template <bool WIDE> struct Map {
   static __device__ __forceinline__ uint32_t addr(uint32_t base, int k, uint32_t stride)
   {
     if (WIDE) return base + (uint32_t)k * stride;
     return (uint32_t)(k >> 2) * stride + (base | (uint32_t)(k & 3));      // the lane's slot is 4-byte aligned
   }
-  // partner << LOG of a MAPPED query SSE: the byte offset of the partner's cell within a row of the entry matrix
+  // 8 * partner of a MAPPED query SSE
   static __device__ __forceinline__ uint32_t off8(uint32_t base, int k, uint32_t stride)
   {
     uint32_t v;
     if (WIDE) asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory");
-    else { asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory"); v <<= LOG; }
+    else { asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory"); v <<= 3; }
     return v;
   }
   // partner of a query SSE, -1 if unmapped
   static __device__ __forceinline__ int get(uint32_t base, int k, uint32_t stride)
   {
     int v;
-    if (WIDE) { asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory"); return v >> LOG; }
+    if (WIDE) { asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory"); return v >> 3; }
     asm("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory");
     return v;
   }
   static __device__ __forceinline__ void put(uint32_t base, int k, uint32_t stride, int j)      // j = -1 unmaps
   {
-    if (WIDE) asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr(base, k, stride)), "r"(j * (1 << LOG)) : "memory");
+    if (WIDE) asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr(base, k, stride)), "r"(j * 8) : "memory");
     else asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr(base, k, stride)), "r"(j) : "memory");
   }
   static __device__ __forceinline__ int words(int n1) { return WIDE ? n1 : (n1 + 3) >> 2; }
@@ -344,36 +336,12 @@ template <bool WIDE, int LOG = 3> struct Map {
   {
 #pragma unroll 1
     for (int w = 0; w < words(n1); w++)
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (uint32_t)w * stride), "r"(WIDE ? -(1 << LOG) : -1) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (uint32_t)w * stride), "r"(WIDE ? -8 : -1) : "memory");
   }
 };
 template <int W1, int W2, bool LORDER, bool XORWOW, bool LSOLN>
 struct Chain {
-  // Entries of more than 32 SSEs (W2 >= 2) come to the production kernels in the SPLIT layout -- per row n2 fp32 distances,
-  // then n2 one-byte codes: 5 instead of 8 bytes per cell, so that more teams' entries fit an SM (these launches are
-  // occupancy-bound by shared memory) -- at the price of two loads per operand.  The validation kernels walk pools of mixed
-  // sizes and always read the 8-byte cells.
-  static constexpr bool SPLIT = SATS_SPLIT_LAYOUT && W2 >= 2 && !XORWOW;
-  typedef Map<(W1 <= 2), (SPLIT ? 2 : 3)> LiveMap;
-  // address of row j of the entry matrix (j = -1: the NaN row)
-  static __device__ __forceinline__ uint32_t entry_row(const TeamView &v, int j)
-  {
-    return SPLIT ? v.ecell + (uint32_t)j * v.erow : v.ecell + (uint32_t)(j * v.n2) * 8u;
-  }
-  // the entry cell in row `row` (a shared-window address) at the column whose byte offset is `off` (LiveMap::off8)
-  static __device__ __forceinline__ uint2 entry_cell(const TeamView &v, uint32_t row, uint32_t off)
-  {
-    if (!SPLIT) return lds64(row + off);
-    uint2 c;
-    c.x = lds32(row + off);
-    asm("ld.shared.u8 %0, [%1];" : "=r"(c.y) : "r"(row + v.ecode + (off >> 2)) : "memory");
-    return c;
-  }
-#ifndef SATS_FLAT_DELTA
-#define SATS_FLAT_DELTA 0
-#endif
-  // cooperative deltasd (delta_flat below): for sparse maps, i.e. LORDER = T, and one-word query masks
-  static constexpr bool FLAT = SATS_FLAT_DELTA && LORDER && W1 == 1;
+  typedef Map<(W1 <= 2)> LiveMap;
   uint32_t mq[W1];   // query SSEs currently mapped
   uint32_t md[W2];   // entry SSEs currently occupied
   int score;
@@ -459,7 +427,7 @@ struct Chain {
       while (bi) {
         int i = 32 * wi + __ffs(bi) - 1;
         bi &= bi - 1u;
-        const uint32_t erow = SPLIT ? entry_row(v, LiveMap::get(v.smap, i, v.mstride)) : v.ecell + LiveMap::off8(v.smap, i, v.mstride) * (uint32_t)v.n2;
+        const uint32_t erow = v.ecell + LiveMap::off8(v.smap, i, v.mstride) * (uint32_t)v.n2;
         const uint32_t qrow = v.qcell + (uint32_t)(i * v.n1) * 8u;
         const uint2 *qrow_g = v.qcell_g + i * v.n1;
 #pragma unroll
@@ -471,7 +439,7 @@ struct Chain {
             int k = 32 * wk + __ffs(bk) - 1;
             bk &= bk - 1u;
             total += gated(W1 > 2 ? with_table<true>(__ldg(qrow_g + k), v.ztab) : lds64(qrow + (uint32_t)k * 8u),
-                           entry_cell(v, erow, LiveMap::off8(v.smap, k, v.mstride)));
+                           lds64(erow + LiveMap::off8(v.smap, k, v.mstride)));
           }
         }
       }
@@ -487,8 +455,8 @@ struct Chain {
     int d = 0;
     const uint2 *qrow_g = v.qcell_g + i * v.n1;                         // W1 == 4: query cells live in global memory
     uint32_t qrow = W1 > 2 ? 0u : v.qcell + (uint32_t)(i * v.n1) * 8u;  // row base addresses, hoisted by hand
-    uint32_t frow = entry_row(v, from);         // from / to = -1: the NaN row in front of the matrix
-    uint32_t trow = entry_row(v, to);
+    uint32_t frow = v.ecell + (uint32_t)(from * v.n2) * 8u;         // from / to = -1: the NaN row in front of the matrix
+    uint32_t trow = v.ecell + (uint32_t)(to * v.n2) * 8u;
     asm volatile("" : "+r"(qrow), "+r"(frow), "+r"(trow));       // keep the compiler from re-folding them into the loop
 #pragma unroll
     for (int w = 0; w < W1; w++) {
@@ -500,58 +468,9 @@ struct Chain {
         const int k = 32 * w + z;
         const uint32_t l8 = LiveMap::off8(v.smap, k, v.mstride);
         const uint2 q = W1 > 2 ? with_table<true>(__ldg(qrow_g + k), v.ztab) : lds64(qrow + (uint32_t)k * 8u);
-        const uint2 ef = entry_cell(v, frow, l8), et = entry_cell(v, trow, l8);
+        const uint2 ef = lds64(frow + l8), et = lds64(trow + l8);
         d += gated(q, et) - gated(q, ef);
       }
-    }
-    return d;
-  }
-
-  // deltasd for the whole warp at once.  With LORDER = T few lanes propose a state-changing move in any one step (~5 of 32,
-  // ~3 mapped partners each), so the per-lane walk above runs with 3-4 active lanes for as many rounds as the busiest lane has
-  // partners.  Here the lanes with a real move publish (partner mask, row addresses) in eight 16-byte slots of shared memory
-  // (slot = rank among the real lanes), every quad of lanes takes one slot and splits its partner mask by bit position
-  // modulo 4, the quad's partial sums meet in two shuffles, and the owner pulls its total from its quad's first lane.  More
-  // than eight real lanes take further passes.  Integer sums: the order of the terms does not matter, results are unchanged.
-  // Every lane of the warp must call this (ballot / shuffles with the full mask).
-  __device__ __forceinline__ int delta_flat(const TeamView &v, int lane, int i, int from, int to) const
-  {
-    const unsigned full = 0xffffffffu;
-    const bool real = (from >= 0) | (to >= 0);
-    const unsigned reals = __ballot_sync(full, real);
-    if (reals == 0u) return 0;
-    const int rank = __popc(reals & ((1u << lane) - 1u)), nreal = __popc(reals);
-    const uint32_t qrow = (v.qcell + (uint32_t)(i * v.n1) * 8u) | ((uint32_t)lane << 24);      // shared-window addresses are < 2^24
-    const uint32_t frow = entry_row(v, from), trow = entry_row(v, to);
-    const uint32_t cls = 0x11111111u << (lane & 3);
-    int d = 0;
-#pragma unroll 1
-    for (int base = 0; base < nreal; base += 8) {
-      const int slot = rank - base;
-      const bool mine = real && (unsigned)slot < 8u;
-      if (mine)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(v.dslot + (uint32_t)slot * 16u), "r"(mq[0] & ~(1u << i)),
-                     "r"(qrow), "r"(frow), "r"(trow) : "memory");
-      __syncwarp();
-      uint32_t b = 0u, oq = 0u, of = 0u, ot = 0u;
-      if (base + (lane >> 2) < nreal)
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(b), "=r"(oq), "=r"(of), "=r"(ot) : "r"(v.dslot + (uint32_t)(lane >> 2) * 16u) : "memory");
-      b &= cls;
-      const uint32_t omap = v.smap + (uint32_t)(((int)(oq >> 24) - lane) * 4);      // the owner's lane-private map
-      oq &= 0xffffffu;
-      int part = 0;
-      while (b) {
-        const int z = top_bit(b);
-        b &= bits_below(z);
-        const uint32_t l8 = LiveMap::off8(omap, z, v.mstride);
-        const uint2 q = lds64(oq + (uint32_t)z * 8u);
-        const uint2 ef = entry_cell(v, of, l8), et = entry_cell(v, ot, l8);
-        part += gated(q, et) - gated(q, ef);
-      }
-      part += __shfl_xor_sync(full, part, 1);
-      part += __shfl_xor_sync(full, part, 2);
-      const int got = __shfl_sync(full, part, (slot & 7) << 2);
-      if (mine) d = got;
     }
     return d;
   }
@@ -560,7 +479,7 @@ struct Chain {
   // returning 32 random bits, so that a sequential generator is advanced exactly when the reference would draw (u2 only
   // with >= 2 candidates).
   template <class U2, class U3>
-  __device__ __forceinline__ void move(const TeamView &v, int m, const SatsKParams &p, int &best, int &best_tag, int tag, int lane,
+  __device__ __forceinline__ void move(const TeamView &v, int m, const SatsKParams &p, int &best, int &best_tag, int tag,
                                        const int i, U2 &&u2, U3 &&u3)
   {
     const bool was_mapped = bit_test<W1>(mq, i);
@@ -599,8 +518,7 @@ struct Chain {
     else if (ncand > 1) to = select_nth<W2>(cand, scaled_index(unit_from_bits(u2()), ncand));
 
     int d = 0;
-    if (FLAT) d = delta_flat(v, lane, i, from, to);
-    else if (from >= 0 || to >= 0) d = delta(v, i, from, to);
+    if (from >= 0 || to >= 0) d = delta(v, i, from, to);
     const int cand_score = score + d;
     const bool improved = cand_score > best;
     if (improved) {
@@ -659,8 +577,8 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
     for (int w = 0; w < W2; w++) asm volatile("st.shared.b32 [%0], %1;" ::"r"(v.qmask + (uint32_t)(k * W2 + w) * 4u), "r"(tm[w]) : "memory");
   }
   if (W1 <= 2) {                                                   // see Chain::move: the window bounds of "nothing mapped below / above"
-    Chain<W1, W2, LORDER, XORWOW, LSOLN>::LiveMap::put(v.smap, -1, v.mstride, v.n2);
-    Chain<W1, W2, LORDER, XORWOW, LSOLN>::LiveMap::put(v.smap, v.n1, v.mstride, -1);
+    Map<true>::put(v.smap, -1, v.mstride, v.n2);
+    Map<true>::put(v.smap, v.n1, v.mstride, -1);
   }
   __syncwarp();
   Chain<W1, W2, LORDER, XORWOW, LSOLN> ch;
@@ -668,14 +586,8 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
   int best_tag = tl;                                  // XORWOW: thread id; Philox: restart index of the best chain
   const int chains = XORWOW ? ((p.restarts + p.tw - 1) / p.tw) * p.tw : p.restarts;
 
-  // The cooperative deltasd needs whole warps: a warp runs while ANY of its lanes has a restart left, the lanes beyond the
-  // last restart run a ghost chain (streams nobody else uses) whose results are discarded.
-  typedef Chain<W1, W2, LORDER, XORWOW, LSOLN> ChainT;
-  for (int r = tl; (ChainT::FLAT ? (r & ~31) : r) < chains; r += p.tw) {
+  for (int r = tl; r < chains; r += p.tw) {
     const int tag = XORWOW ? tl : r;
-    const bool ghost = ChainT::FLAT && r >= chains;
-    const int best_so_far = best;
-    if (ghost) best = 0x3fffffff;                      // nothing a ghost finds can improve on this
     if (XORWOW) {
       ch.seed(v, [&](int) { return xw.next() < p.seed_cut; });
     } else {
@@ -693,7 +605,7 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
     }
     if (XORWOW) {
       for (int m = 0; m < SATS_K_MOVES; m++)
-        ch.move(v, m, p, best, best_tag, tag, tl & 31, pick_index(xw.next(), v.n1, v.pick_cut), [&] { return xw.next(); }, [&] { return xw.next(); });
+        ch.move(v, m, p, best, best_tag, tag, pick_index(xw.next(), v.n1, v.pick_cut), [&] { return xw.next(); }, [&] { return xw.next(); });
     } else {
       // static draw positions: Philox block g feeds moves 2g (words 0, 1) and 2g + 1 (words 2, 3); per move the first word
       // picks the SSE (and, hashed, the candidate), the second is the Metropolis draw
@@ -705,14 +617,13 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
         // the SSE picks depend on the draws only, not on the chains' state: issued together, off the moves' critical path
         const int i0 = pick_index(a[0], v.n1, v.pick_cut), i1 = pick_index(a[2], v.n1, v.pick_cut);
         const int i2 = pick_index(b[0], v.n1, v.pick_cut), i3 = pick_index(b[2], v.n1, v.pick_cut);
-        ch.move(v, m + 0, p, best, best_tag, tag, tl & 31, i0, [&] { return candidate_bits(a[0]); }, [&] { return a[1]; });
-        ch.move(v, m + 1, p, best, best_tag, tag, tl & 31, i1, [&] { return candidate_bits(a[2]); }, [&] { return a[3]; });
-        ch.move(v, m + 2, p, best, best_tag, tag, tl & 31, i2, [&] { return candidate_bits(b[0]); }, [&] { return b[1]; });
-        ch.move(v, m + 3, p, best, best_tag, tag, tl & 31, i3, [&] { return candidate_bits(b[2]); }, [&] { return b[3]; });
+        ch.move(v, m + 0, p, best, best_tag, tag, i0, [&] { return candidate_bits(a[0]); }, [&] { return a[1]; });
+        ch.move(v, m + 1, p, best, best_tag, tag, i1, [&] { return candidate_bits(a[2]); }, [&] { return a[3]; });
+        ch.move(v, m + 2, p, best, best_tag, tag, i2, [&] { return candidate_bits(b[0]); }, [&] { return b[1]; });
+        ch.move(v, m + 3, p, best, best_tag, tag, i3, [&] { return candidate_bits(b[2]); }, [&] { return b[3]; });
       }
     }
     if (LSOLN) ch.finish_best_map(v);
-    if (ghost) best = best_so_far;
   }
 
   // ---- arg-max over the team: highest score, lowest tag (kernel.cu:1205-1221 scans thread 0..127 with '>')
@@ -790,8 +701,7 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
   v.bmap = smem_u32(bmaps + tl * 4);
   // team scratch: red[2][4] (two alternating arg-max buffers) | claim[2] | per-warp qmask copies
   volatile int *claim = reinterpret_cast<volatile int *>(red + 8);
-  v.dslot = smem_u32(reinterpret_cast<uint8_t *>(red) + SATS_K_SCRATCH_BYTES + (tl >> 5) * p.sm_qmask_bytes);     // per warp: slots, then qmask
-  v.qmask = v.dslot + SATS_K_DSLOT_BYTES;
+  v.qmask = smem_u32(reinterpret_cast<uint8_t *>(red) + SATS_K_SCRATCH_BYTES + (tl >> 5) * p.sm_qmask_bytes);
   Xorwow xw;
 
   if (!XORWOW) {
@@ -820,10 +730,9 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
     auto fetch = [&](int idx) {
       if (idx < p.item_count) {
         const int e = p.item_first + idx;
-        const bool split = Chain<W1, W2, LORDER, false, LSOLN>::SPLIT;
-        const uint32_t bytes = split ? p.blob_bytes_split[e] : p.blob_bytes[e];
+        const uint32_t bytes = p.blob_bytes[e];
         mbar_expect_tx(tbar, bytes);
-        tma_load_1d(se, p.blobs + (split ? p.blob_off_split[e] : p.blob_off[e]), bytes, tbar);
+        tma_load_1d(se, p.blobs + p.blob_off[e], bytes, tbar);
       }
     };
     if (tl == 0) fetch(claim_next(0));
@@ -838,13 +747,7 @@ __global__ void __launch_bounds__(SATS_K_MAXTHREADS, SATS_K_MINBLOCKS) sats_anne
       mbar_wait(tbar, phase);
       phase ^= 1u;
       v.n2 = eh[0];
-      if (Chain<W1, W2, LORDER, false, LSOLN>::SPLIT) {
-        v.ecode = 4u * (uint32_t)v.n2;
-        v.erow = v.ecode + (((uint32_t)v.n2 + 3u) & ~3u);
-        v.ecell = ecell0 + v.erow;
-      } else {
-        v.ecell = ecell0 + 8u * (uint32_t)v.n2;
-      }
+      v.ecell = ecell0 + 8u * (uint32_t)v.n2;
       anneal_entry<W1, W2, LORDER, false, LSOLN>(p, v, team, tl, red + 4 * par, (uint32_t)eh[1], p.q_index_base + (uint32_t)qh[1], xw, qi, p.item_first + idx,
                                                  [&] { if (tl == 0) claim_next(par ^ 1); },
                                                  [&] { if (tl == 0) fetch(claim[par ^ 1]); });

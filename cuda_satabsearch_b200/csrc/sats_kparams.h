@@ -15,7 +15,6 @@
 #define SATS_K_BAR_BYTES 128       // shared-memory header: 1 + teams mbarriers (teams <= 12)
 #define SATS_K_ZTAB_BYTES 256      // shared-memory room for the 128-byte zeta table at a 128-byte aligned address
 #define SATS_K_SCRATCH_BYTES 80     // per team: two alternating arg-max buffers (4 x 8 B each) and two claim slots
-#define SATS_K_DSLOT_BYTES 128     // per warp: eight 16-byte slots of the cooperative deltasd (Chain::delta_flat)
 #define SATS_K_MAPROW 112          // bytes per (query, entry) row of the device map output
 
 struct SatsKParams {
@@ -23,8 +22,6 @@ struct SatsKParams {
   const uint8_t *blobs;            // entry blobs, each 16-byte aligned
   const uint64_t *blob_off;        // byte offset of entry k
   const uint32_t *blob_bytes;      // size of entry k's blob (multiple of 16)
-  const uint64_t *blob_off_split;  // the same for the split layout (entries of more than 32 SSEs have a second blob: per row n2 fp32
-  const uint32_t *blob_bytes_split;//   distances, then n2 code bytes); entries of <= 32 SSEs point at their one and only blob
   // queries of this launch: blockIdx.y selects one
   const uint8_t *qblobs;
   const uint64_t *qblob_off;
@@ -46,7 +43,7 @@ struct SatsKParams {
   int sm_entry_bytes;              // room for the largest entry blob of this launch
   int sm_mapwords;                 // 32-bit words per live chain map: n1max (queries of <= 64 SSEs) or ceil(n1max / 4)
   int sm_bmapwords;                // 32-bit words per best map: ceil(n1max / 4) with lsoln, else 0
-  int sm_qmask_bytes;              // per warp: SATS_K_DSLOT_BYTES + room for n1max x W2 words (16-byte multiple)
+  int sm_qmask_bytes;              // per warp: room for n1max x W2 words (16-byte multiple)
   int sm_team_bytes;               // total per team
   // search parameters
   int restarts, lsoln, accept_mode;
