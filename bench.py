@@ -245,6 +245,17 @@ CONFIG = {"workload": "D2PHLB1 (n1=19, T T F) vs synthetic 100k-structure db (bo
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def gather_plan(idx_all: np.ndarray, db_size: int) -> np.ndarray:
+    """idx_all: the ranks' padded entry-index vectors laid end to end (original db index of every gathered slot, -1 =
+    padding).  Returns `take` with scores_by_original_index = gathered[take]; checks that the shards tile the database."""
+    valid = np.nonzero(idx_all >= 0)[0]
+    if len(valid) != db_size or len(np.unique(idx_all[valid])) != db_size:
+        raise RuntimeError("the shards do not tile the database: %d slots for %d structures" % (len(valid), db_size))
+    take = np.empty(db_size, np.int64)
+    take[idx_all[valid]] = valid
+    return take
+
+
 def ours(args):
     import torch
     import cuda_satabsearch_b200 as S
@@ -322,11 +333,7 @@ def ours(args):
         idx_all = [torch.empty_like(idx_pad) for _ in range(n_gpus)] if rank == 0 else None
         dist.gather(idx_pad, idx_all, dst=0)
         if rank == 0:
-            idx_host = torch.cat(idx_all).cpu().numpy()
-            valid = np.nonzero(idx_host >= 0)[0]
-            assert len(valid) == DB_SIZE and len(np.unique(idx_host[valid])) == DB_SIZE
-            take = np.empty(DB_SIZE, np.int64)          # original index -> position in the gathered buffer
-            take[idx_host[valid]] = valid
+            take = gather_plan(torch.cat(idx_all).cpu().numpy(), DB_SIZE)      # original index -> position in the gathered buffer
             gathered = torch.empty(n_gpus * cap, dtype=torch.int32, device=dev)
             host = torch.empty(n_gpus * cap, dtype=torch.int32).pin_memory()
         else:

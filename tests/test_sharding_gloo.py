@@ -35,6 +35,23 @@ def _worker(rank, world, port, out_path):
     merged = torch.full((len(ents),), -(2 ** 31), dtype=torch.int32)
     merged[torch.from_numpy(mine.astype(np.int64))] = torch.from_numpy(sc)
     dist.all_reduce(merged, op=dist.ReduceOp.MAX)            # disjoint shards: MAX == gather by original index
+    # bench.py's N > 1 end-to-end tail: every rank contributes its scores in DEVICE order (decreasing structure order) padded
+    # to the largest shard, one all-gather, rank 0 un-permutes with the plan built once from the ranks' entry indices
+    import bench
+    orders = np.array([s.n for s in ents])
+    dev = mine[np.argsort(-orders[mine], kind="stable")]
+    by_orig = dict(zip(mine.tolist(), sc.tolist()))
+    cap_t = torch.tensor([len(mine)]); dist.all_reduce(cap_t, op=dist.ReduceOp.MAX)
+    cap = int(cap_t.item())
+    idx_pad = torch.full((cap,), -1, dtype=torch.int32); idx_pad[:len(dev)] = torch.from_numpy(dev)
+    sc_pad = torch.zeros(cap, dtype=torch.int32); sc_pad[:len(dev)] = torch.tensor([by_orig[int(e)] for e in dev], dtype=torch.int32)
+    idx_all = [torch.empty_like(idx_pad) for _ in range(world)]
+    sc_all = [torch.empty_like(sc_pad) for _ in range(world)]
+    dist.all_gather(idx_all, idx_pad)
+    dist.all_gather(sc_all, sc_pad)
+    take = bench.gather_plan(torch.cat(idx_all).numpy(), len(ents))
+    assembled = np.take(torch.cat(sc_all).numpy(), take)
+    assert np.array_equal(assembled, merged.numpy()), "all-gather + plan must equal the merge by original index"
     t = torch.tensor([10.0 + rank], dtype=torch.float64)     # per-rank "device time"
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     cnt = torch.tensor([len(mine)]); dist.all_reduce(cnt)
