@@ -308,8 +308,8 @@ def ours(args):
     # ---- end to end: host query in, ALL scores in one host buffer out.
     # N = 1: the public one-shot call sats_search() (query H2D, kernels, scores D2H, scatter to original order).
     # N > 1: every rank uploads the query and searches its shard; the shards' int32 score vectors are then gathered to
-    #        rank 0 over NCCL straight from the searchers' device buffers ("one tiny gather after"), copied to
-    #        the host once and scattered by original index -- so a step ends with the full 100k-score row on rank 0.
+    #        rank 0 over NCCL straight from the searchers' device buffers ("one tiny gather after"), brought into
+    #        original db order on the device and copied to the host once -- a step ends with the full 100k-score row on rank 0.
     gather_ms = 0.0
     if dist is None:
         barrier()
@@ -334,8 +334,11 @@ def ours(args):
         dist.gather(idx_pad, idx_all, dst=0)
         if rank == 0:
             take = gather_plan(torch.cat(idx_all).cpu().numpy(), DB_SIZE)      # original index -> position in the gathered buffer
+            take_dev = torch.from_numpy(take).to(dev)
             gathered = torch.empty(n_gpus * cap, dtype=torch.int32, device=dev)
-            host = torch.empty(n_gpus * cap, dtype=torch.int32).pin_memory()
+            ordered = torch.empty(DB_SIZE, dtype=torch.int32, device=dev)
+            host = torch.empty(DB_SIZE, dtype=torch.int32).pin_memory()
+            scores = host.numpy().reshape(1, DB_SIZE)            # the step's result buffer: pinned, filled by one D2H copy
         else:
             gathered = torch.empty(n_gpus * cap, dtype=torch.int32, device=dev)
         pad = torch.zeros(cap, dtype=torch.int32, device=dev)
@@ -352,9 +355,9 @@ def ours(args):
             pad[:n].copy_(view[ptr])
             dist.all_gather_into_tensor(gathered, pad)          # one NCCL collective; every shard is ~4 B x D / N
             if rank == 0:
-                host.copy_(gathered, non_blocking=True)
+                torch.index_select(gathered, 0, take_dev, out=ordered)      # un-permute to original db order on the device
+                host.copy_(ordered, non_blocking=True)
                 torch.cuda.synchronize()
-                np.take(host.numpy(), take, out=scores[0])
             else:
                 torch.cuda.synchronize()
             return (time.perf_counter() - g0) * 1e3 if timed_gather else 0.0
@@ -366,7 +369,7 @@ def ours(args):
             gather_ms += step(True)
         barrier()
         e2e_ms = (time.perf_counter() - e0) * 1e3
-        d2h_bytes = 4 * n_gpus * cap
+        d2h_bytes = 4 * DB_SIZE
         if rank == 0:                    # the assembled row must be the unsharded result: spot-check against one local search
             ref_row = np.full((1, len(db)), np.iinfo(np.int32).min, np.int32)
             sr.search(qs, p, scores=ref_row)
@@ -442,8 +445,9 @@ def ours(args):
                 "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_ms / args.steps,
                 "gather_ms_per_step": (gather_ms / args.steps) if n_gpus > 1 else None,
                 "path": "sats_search(): host query in, host scores out" if n_gpus == 1 else
-                        "per rank upload + launch; NCCL all-gather of the shards' device score vectors; one D2H copy on rank 0; "
-                        "scatter by original index (gather_ms_per_step = that tail, rank 0)"},
+                        "per rank upload + launch; NCCL all-gather of the shards' device score vectors; rank 0 un-permutes them "
+                        "to original db order on the device and copies the 100k scores to pinned host memory "
+                        "(gather_ms_per_step = that tail, rank 0)"},
         "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
         "reference_gpu_same_box": ref_gpu,
         "local_entries_rank0": n_local,

@@ -123,3 +123,42 @@ def test_database_orders_above_111(synth, oracle, lorder, lsoln, restarts, tmp_p
     write_ascii_db(tmp_path / "big.ascii", small_d)
     assert len(S.Database.read_ascii(tmp_path / "big.ascii")) == 4
     assert len(S.Database.read_ascii(tmp_path / "big.ascii", max_order=S.MAXDIM_EXT)) == 10
+
+
+def test_device_results_and_overlapped_collect(fixtures):
+    """The multi-GPU host calls of round 2: sats_device_init, sats_search_collect_begin (copy-back enqueued, no wait), and the
+    device-resident results a caller gathers with its own collective (sats_search_device_results + sats_searcher_entry_index):
+    read straight from the device pointer they must be the scores collect() delivers, column k = original entry index[k]."""
+    import torch
+    ents = fixtures["small586"][:200]
+    qs = [fixtures["queries_by_name"][n] for n in ("D2PHLB1", "D1UBIA_", "SHEETBC")]      # two size classes -> slots are reordered
+    db = S.Database.from_structures([s.name for s in ents], [s.tab for s in ents], [s.dmat for s in ents])
+    q = S.Database.from_structures([s.name for s in qs], [s.tab for s in qs], [s.dmat for s in qs])
+    assert S.lib().sats_device_init(0) == 0 and S.lib().sats_device_init(99) < 0
+    shards = [S.Searcher(db, 0, r, 2) for r in range(2)]
+    p = S.default_params(lorder=1, lsoln=0, restarts=64, seed=8)
+    want, _ = S.Searcher(db, 0).search(q, p)
+    merged = np.full_like(want, -1)
+    via_device = np.full_like(want, -1)
+    for sr in shards:
+        sr.upload(q)
+        sr.launch(p, 0)
+    for sr in shards:
+        sr.collect_begin()
+    for sr in shards:
+        sr.collect(scores=merged)
+        sr.sync()
+        ptr, nq, ne, slots = sr.device_results()
+        assert nq == 3 and ne == sr.entries and sorted(slots.tolist()) == [0, 1, 2]
+
+        class Dev:
+            __cuda_array_interface__ = {"shape": (nq * ne,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+        rows = torch.as_tensor(Dev(), device="cuda:0").cpu().numpy().reshape(nq, ne)
+        idx = sr.entry_index()
+        orders = np.array([ents[i].n for i in idx])
+        assert (np.diff(orders) <= 0).all()                      # device order = decreasing structure order
+        for slot in range(nq):
+            via_device[slots[slot], idx] = rows[slot]
+    assert np.array_equal(merged, want) and np.array_equal(via_device, want)
+    for sr in shards:
+        sr.close()
