@@ -163,6 +163,9 @@ template <int W> __device__ __forceinline__ int select_nth(const uint32_t (&c)[W
       }
     }
   }
+  // kept rolled: idx is 0..2 almost always (two or three candidates), and the unrolled-by-four form ptxas makes of this loop
+  // runs ~25 instructions of remainder handling for the handful of lanes that get here
+#pragma unroll 1
   for (; idx > 0; idx--) word &= word - 1u;
   return base + __ffs(word) - 1;
 }
