@@ -377,7 +377,11 @@ def ours(args):
             assert np.array_equal(scores[0, mine], ref_row[0, mine]) and scores.min() > np.iinfo(np.int32).min
     clk = clocks.stop() if rank == 0 else None
 
+    rank_ms = [dev_ms / args.steps]
     if dist is not None:
+        every = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(n_gpus)]
+        dist.all_gather(every, torch.tensor([dev_ms / args.steps], device=dev, dtype=torch.float64))
+        rank_ms = [float(x) for x in every]            # device-timed ms per step of every rank: the spread is the load imbalance
         t = torch.tensor([dev_ms, e2e_ms, float(launches), wall_ms], device=dev, dtype=torch.float64)
         mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
@@ -450,7 +454,7 @@ def ours(args):
                         "(gather_ms_per_step = that tail, rank 0)"},
         "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
         "reference_gpu_same_box": ref_gpu,
-        "local_entries_rank0": n_local,
+        "local_entries_rank0": n_local, "rank_ms_per_step": rank_ms,
     }
     print(json.dumps(line))
     if dist is not None:
