@@ -312,17 +312,19 @@ try {
   };
   {
     const size_t nthreads = total < (8u << 20) ? 1 : std::max<size_t>(1, std::min<size_t>(8, std::thread::hardware_concurrency()));
-    std::vector<std::thread> pool;
+    struct Joiner {                                  // joins whatever was started, also when starting a thread throws
+      std::vector<std::thread> pool;
+      ~Joiner() { for (auto &th : pool) if (th.joinable()) th.join(); }
+    } workers;
     size_t k0 = 0;
     for (size_t t = 0; t < nthreads; t++) {          // equal BYTES per thread (the list is sorted by decreasing size)
       size_t k1 = k0;
       const uint64_t upto = total / nthreads * (t + 1);
       while (k1 < local.size() && (t + 1 == nthreads || off[k1] < upto)) k1++;
       if (t + 1 == nthreads) fill_range(k0, local.size());
-      else pool.emplace_back(fill_range, k0, k1);
+      else workers.pool.emplace_back(fill_range, k0, k1);
       k0 = k1;
     }
-    for (auto &th : pool) th.join();
   }
   TRACE("blob fill");
   auto fail = [&](int rc) { sats_searcher_free(s); return rc; };
@@ -829,7 +831,7 @@ try {
         }
         CK(cudaGraphLaunch(s->graph_exec, s->stream));
         key.ptr[8] = s->d_counters;          // may have been (re)allocated above
-        s->graph_key = key;
+        memcpy(&s->graph_key, &key, sizeof key);      // byte copy: the comparison above is a memcmp, padding included
         s->graph_key_valid = true;
       }
       s->launches += (long long)plan.size();
