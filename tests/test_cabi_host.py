@@ -287,3 +287,18 @@ def test_shim_checks_caller_buffers():
     for bad in (np.zeros((2, 5), np.float64), np.zeros((2, 4), np.int32), np.zeros((5, 2), np.int32).T, np.zeros((2, 10), np.int32)[:, ::2]):
         with pytest.raises(S.SatsError, match="scores must be"):
             _out_array(bad, (2, 5), "scores")
+
+
+def test_result_printer_tail_cache_is_transparent():
+    """sats_format_block memoizes the numeric columns per (score, structure order); with far more distinct pairs than the
+    cache holds (and negative scores) every row must still be what printf makes of it."""
+    db = S.Database.read_packed(GOLDEN / "small586.satsdb").bootstrap(30000, 3, False)
+    rng = np.random.default_rng(9)
+    sc = rng.integers(-3000, 12000, len(db)).astype(np.int32)
+    txt = db.format_block("QUERYID", 23, "some/db.ascii", True, False, sc)
+    rows = txt.split("\n")
+    assert rows[1] == "# QUERY ID = QUERYID " and len(rows) == 3 + len(db) + 1
+    orders = db.orders()
+    for k in list(range(0, len(db), 7)) + [len(db) - 1]:
+        n2s, z, p = stats(int(sc[k]), 23, int(orders[k]))
+        assert rows[3 + k] == "%-8s %d %g %g %g" % (db.name(k), int(sc[k]), n2s, z, p), k
