@@ -63,3 +63,36 @@ def test_xorwow_stream0_is_seed_scramble(oracle):
     x[0] = (x[0] + 362437) & 0xffffffff
     got = oracle.lib.sats_oracle_xorwow_next(s.ctypes.data)
     assert got == (x[5] + x[0]) & 0xffffffff and s.tolist() == x
+
+
+def test_stream_layout_v2_candidate_draw_is_uniform_given_the_pick(oracle):
+    """Production streams, layout v2: one 32-bit word picks the query SSE (its leading bits decide) and, Fibonacci-hashed
+    (word * 0x9E3779B9), also draws the candidate.  For that to be sound the hashed draw must be uniform CONDITIONAL on the
+    pick -- checked here for every pick value of a small, the bench and the largest query: chi-square of the candidate index
+    over 2..7 candidates, and the correlation of the two uniforms."""
+    pick = oracle.lib.sats_oracle_pick_from_bits
+    rng = np.random.default_rng(2024)
+    x = rng.integers(0, 2**32, 400000, dtype=np.uint64)
+    u1 = (x.astype(np.float32) * np.float32(2.3283064e-10) + np.float32(1.1641532e-10)).astype(np.float64)
+    h = (x * np.uint64(0x9E3779B9)) & np.uint64(0xffffffff)
+    u2 = (h.astype(np.float32) * np.float32(2.3283064e-10) + np.float32(1.1641532e-10)).astype(np.float64)
+    assert abs(np.corrcoef(u1, u2)[0, 1]) < 0.01
+    for n1 in (8, 19, 111):
+        i = np.minimum(((u1 - 1.1e-7) * n1).astype(np.int64), n1 - 1)
+        i = np.maximum(i, 0)
+        for k in (0, n1 // 2, n1 - 1):
+            assert pick(int(x[k]), n1) == int(i[k])                      # the vectorised pick is the oracle's
+        for ncand in (2, 3, 7):
+            c = np.maximum(((u2 - 1.1e-7) * ncand).astype(np.int64), 0)
+            for iv in range(n1):
+                sel = c[i == iv]
+                if len(sel) < 1500:
+                    continue
+                obs = np.bincount(sel, minlength=ncand).astype(np.float64)
+                exp = len(sel) / ncand
+                chi2 = ((obs - exp) ** 2 / exp).sum()
+                assert chi2 < 40.0, (n1, ncand, iv, obs)                # 6 degrees of freedom at most: p < 1e-6 if it failed
+    # and the seeding bits: one bit per query SSE, all 128 of a block usable
+    ctr, key = [0x80000000, 5, 77, 3], [1234, 0]
+    words = oracle.philox(ctr, key)
+    assert len(words) == 4 and all(0 <= w < 2**32 for w in words)
