@@ -57,6 +57,7 @@ def _load() -> C.CDLL:
         "sats_db_read_packed": (ci, [cs, P(vp)]),
         "sats_tabcode_from_angle": (ci, [C.c_double, cs]), "sats_relative_angle": (ci, [vp, vp, vp, vp, P(C.c_double)]),
         "sats_build_structure": (ci, [cs, ci, vp, vp, vp, P(vp)]),
+        "sats_fit_axis": (ci, [ci, ci, vp, vp, vp]), "sats_build_structure_from_ca": (ci, [cs, ci, vp, vp, vp, P(vp)]),
         "sats_norm2": (C.c_double, [ci, ci, ci]), "sats_z_gumbel": (C.c_double, [ci, C.c_double, C.c_double]),
         "sats_pv_gumbel": (C.c_double, [C.c_double]),
         "sats_format_block": (C.c_size_t, [vp, C.c_size_t, cs, ci, cs, ci, ci, vp, vp, ci, vp, vp]),
@@ -278,6 +279,27 @@ def build_structure(name: str, sse_types, centroids, dircos) -> Database:
         raise SatsError("centroids and dircos must be (n, 3) arrays matching sse_types")
     h = C.c_void_p()
     _check(lib().sats_build_structure(name.encode(), len(t), t.ctypes.data, c.ctypes.data, d.ctypes.data, C.byref(h)))
+    return Database(h.value)
+
+
+def fit_axis(sse_type: int, ca_xyz):
+    """scripts/ptnode.py fit_axis on a C-alpha trace (n_res x 3) -> (dircos, centroid) or None where the reference gives None."""
+    ca = np.ascontiguousarray(ca_xyz, np.float64).reshape(-1, 3)
+    d = np.zeros(3); c = np.zeros(3)
+    rc = _check(lib().sats_fit_axis(int(sse_type), len(ca), ca.ctypes.data, d.ctypes.data, c.ctypes.data))
+    return None if rc == 1 else (d, c)
+
+
+def build_structure_from_ca(name: str, sse_types, ca_traces) -> Database:
+    """A one-structure Database from the SSEs' C-alpha traces (a list of (n_res, 3) arrays, N- to C-terminus)."""
+    t = np.ascontiguousarray(sse_types, np.uint8)
+    traces = [np.ascontiguousarray(x, np.float64).reshape(-1, 3) for x in ca_traces]
+    if len(traces) != len(t):
+        raise SatsError("one C-alpha trace per SSE")
+    nres = np.array([len(x) for x in traces], np.int32)
+    ca = np.ascontiguousarray(np.concatenate(traces)) if traces else np.zeros((1, 3))
+    h = C.c_void_p()
+    _check(lib().sats_build_structure_from_ca(name.encode(), len(t), t.ctypes.data, nres.ctypes.data, ca.ctypes.data, C.byref(h)))
     return Database(h.value)
 
 

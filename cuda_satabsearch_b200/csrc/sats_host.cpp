@@ -618,9 +618,9 @@ extern "C" int sats_relative_angle(const double c_self[3], const double d_self[3
 // compute_sse_midpoint_dist_matrix (scripts/ptdistmatrix.py:1014-1066), then the writer's conventions -- "%6.3f" text that the
 // search program reads back with strtof (scripts/convdb2.py:213-231), NaN -> 0.000, distances above 99.9 A clamped to 99.9
 // (scripts/pytableaucreate.py:114-116; wider values break the 7-column format).
-extern "C" int sats_build_structure(const char *name, int n, const uint8_t *sse_type, const double *centroid,
-                                    const double *dircos, sats_db **out)
-try {
+static int build_structure_impl(const char *name, int n, const uint8_t *sse_type, const double *centroid, const double *dircos,
+                                const uint8_t *has_axis, sats_db **out)
+{
   if (!name || !sse_type || !centroid || !dircos || !out) return sats_fail(SATS_ERR_ARG, "sats_build_structure: null argument");
   if (n < 1 || n > SATS_MAXDIM) return sats_fail(SATS_ERR_ARG, "sats_build_structure: order %d outside 1..%d", n, SATS_MAXDIM);
   std::vector<uint8_t> tab((size_t)n * (n + 1) / 2);
@@ -641,7 +641,8 @@ try {
     for (int j = i + 1; j < n; j++) {
       double omega = 0.0;
       int code = 0x44;                                         // "??": no angle (the reference leaves the entry unset)
-      const int rc = sats_relative_angle(centroid + 3 * i, dircos + 3 * i, centroid + 3 * j, dircos + 3 * j, &omega);
+      const bool axes = !has_axis || (has_axis[i] && has_axis[j]);        // an SSE without an axis: fit_axis() returned None
+      const int rc = axes ? sats_relative_angle(centroid + 3 * i, dircos + 3 * i, centroid + 3 * j, dircos + 3 * j, &omega) : 1;
       if (rc < 0) return rc;
       if (rc == 0) {
         char c2[3];
@@ -654,12 +655,142 @@ try {
       const double dx = centroid[3 * i] - centroid[3 * j], dy = centroid[3 * i + 1] - centroid[3 * j + 1],
                    dz = centroid[3 * i + 2] - centroid[3 * j + 2];
       tab[(size_t)j * (j + 1) / 2 + i] = (uint8_t)code;
-      dm[(size_t)j * (j + 1) / 2 + i] = as_written(std::sqrt(dx * dx + dy * dy + dz * dz));
+      // calc_sse_sse_midpoint_dist returns None without both axes; the matrix then holds NaN, written as 0.000
+      dm[(size_t)j * (j + 1) / 2 + i] = as_written(axes ? std::sqrt(dx * dx + dy * dy + dz * dz) : NAN);
     }
   std::unique_ptr<sats_db> db(new sats_db());
   db->append(name, n, tab.data(), dm.data());
   *out = db.release();
   return SATS_OK;
+}
+
+extern "C" int sats_build_structure(const char *name, int n, const uint8_t *sse_type, const double *centroid,
+                                    const double *dircos, sats_db **out)
+try {
+  return build_structure_impl(name, n, sse_type, centroid, dircos, nullptr, out);
+}
+SATS_CATCH_ALL
+
+// scripts/ptnode.py:1113-1292 (PTNodeHelix.fit_axis) and :1846-1990 (PTNodeStrand.fit_axis): the axis of an SSE as a total
+// least squares line through points derived from its C-alpha trace -- helices: the midpoints of the planes of consecutive
+// C-alpha triples; strands: the midpoints of consecutive C-alpha pairs (to take out the pleat), centred on the C-alpha
+// centroid.  The direction is the first right singular vector of the centred points (here: the dominant eigenvector of their
+// 3 x 3 scatter matrix, by Jacobi rotations), oriented from the N- to the C-terminus.  Short SSEs fall back to the line through
+// two midpoints / two atoms; returns 1 where the reference returns None (helix of < 3 residues, strand of 1).
+namespace {
+V3 dominant_direction(const std::vector<V3> &pts)
+{
+  double a[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (const V3 &p : pts) {
+    const double c[3] = {p.x, p.y, p.z};
+    for (int r = 0; r < 3; r++)
+      for (int q = 0; q < 3; q++) a[r][q] += c[r] * c[q];
+  }
+  for (int sweep = 0; sweep < 64; sweep++) {                    // cyclic Jacobi on the symmetric 3 x 3 scatter matrix
+    const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+    if (off < 1e-300) break;
+    for (int p = 0; p < 2; p++)
+      for (int q = p + 1; q < 3; q++) {
+        if (a[p][q] == 0.0) continue;
+        const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < 3; k++) {                            // A <- A J
+          const double akp = a[k][p], akq = a[k][q];
+          a[k][p] = c * akp - sn * akq;
+          a[k][q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < 3; k++) {                            // A <- J^T A
+          const double apk = a[p][k], aqk = a[q][k];
+          a[p][k] = c * apk - sn * aqk;
+          a[q][k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; k++) {                            // V <- V J
+          const double vkp = v[k][p], vkq = v[k][q];
+          v[k][p] = c * vkp - sn * vkq;
+          v[k][q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  int best = 0;
+  for (int k = 1; k < 3; k++) if (a[k][k] > a[best][best]) best = k;
+  return unit(V3{v[0][best], v[1][best], v[2][best]});
+}
+}  // namespace
+
+extern "C" int sats_fit_axis(int sse_type, int n_res, const double *ca_xyz, double dircos[3], double centroid[3])
+try {
+  if (!ca_xyz || !dircos || !centroid || n_res < 0 || sse_type < 0 || sse_type > 3) return sats_fail(SATS_ERR_ARG, "sats_fit_axis: bad argument");
+  auto ca = [&](int i) { return V3{ca_xyz[3 * i], ca_xyz[3 * i + 1], ca_xyz[3 * i + 2]}; };
+  auto mid = [&](V3 a, V3 b) { return V3{(b.x - a.x) / 2 + a.x, (b.y - a.y) / 2 + a.y, (b.z - a.z) / 2 + a.z}; };
+  auto mean = [&](const std::vector<V3> &p) {
+    V3 c{0, 0, 0};
+    for (const V3 &q : p) { c.x += q.x; c.y += q.y; c.z += q.z; }
+    return V3{c.x / (double)p.size(), c.y / (double)p.size(), c.z / (double)p.size()};
+  };
+  std::vector<V3> pts;
+  V3 cen{0, 0, 0}, dir{0, 0, 0}, nterm{0, 0, 0}, cterm{0, 0, 0};
+  bool fitted = false;
+  if (sse_type != 0) {                                            // helix (alpha, pi, 3-10)
+    if (n_res < 3) return 1;
+    if (n_res == 3) {
+      const V3 mp1 = mid(ca(0), ca(1)), mp2 = mid(ca(1), ca(2));
+      cen = V3{(mp1.x + mp2.x) / 2, (mp1.y + mp2.y) / 2, (mp1.z + mp2.z) / 2};
+      dir = unit(mp2 - mp1);
+    } else {
+      for (int i = 1; i + 1 < n_res; i++) {                       // midpoint of the plane of C-alphas i-1, i, i+1
+        const V3 v1 = ca(i - 1) - ca(i), v2 = ca(i + 1) - ca(i);
+        pts.push_back(V3{ca(i).x + (v1.x + v2.x) / 2, ca(i).y + (v1.y + v2.y) / 2, ca(i).z + (v1.z + v2.z) / 2});
+      }
+      cen = mean(pts);
+      nterm = pts.front(); cterm = pts.back();
+      for (V3 &q : pts) q = q - cen;
+      fitted = true;
+    }
+  } else {                                                        // strand
+    if (n_res < 2) return 1;
+    std::vector<V3> atoms;
+    for (int i = 0; i < n_res; i++) atoms.push_back(ca(i));
+    cen = mean(atoms);
+    if (n_res == 2) dir = unit(ca(1) - ca(0));
+    else if (n_res == 3) dir = unit(mid(ca(1), ca(2)) - mid(ca(0), ca(1)));
+    else {
+      for (int i = 0; i + 1 < n_res; i++) pts.push_back(mid(ca(i), ca(i + 1)) - cen);
+      nterm = ca(0); cterm = ca(n_res - 1);
+      fitted = true;
+    }
+  }
+  if (fitted) {
+    dir = dominant_direction(pts);
+    // orientation: N- to C-terminus (the reference projects both ends onto the line and tests the angle for pi)
+    if (dot(cterm - nterm, dir) < 0) dir = V3{-dir.x, -dir.y, -dir.z};
+  }
+  dircos[0] = dir.x; dircos[1] = dir.y; dircos[2] = dir.z;
+  centroid[0] = cen.x; centroid[1] = cen.y; centroid[2] = cen.z;
+  return SATS_OK;
+}
+SATS_CATCH_ALL
+
+// C-alpha traces of the SSEs -> searchable structure: sats_fit_axis per SSE, then sats_build_structure; an SSE whose axis cannot
+// be fitted keeps "??" codes and 0.000 distances against everything, as the reference's None propagates.
+extern "C" int sats_build_structure_from_ca(const char *name, int n, const uint8_t *sse_type, const int32_t *n_res,
+                                            const double *ca_xyz, sats_db **out)
+try {
+  if (!name || !sse_type || !n_res || !ca_xyz || !out) return sats_fail(SATS_ERR_ARG, "sats_build_structure_from_ca: null argument");
+  if (n < 1 || n > SATS_MAXDIM) return sats_fail(SATS_ERR_ARG, "sats_build_structure_from_ca: order %d outside 1..%d", n, SATS_MAXDIM);
+  std::vector<double> cen(3 * (size_t)n, 0.0), dir(3 * (size_t)n, 0.0);
+  std::vector<uint8_t> has((size_t)n, 0);
+  size_t at = 0;
+  for (int i = 0; i < n; i++) {
+    if (n_res[i] < 0) return sats_fail(SATS_ERR_ARG, "sats_build_structure_from_ca: SSE %d has %d residues", i, n_res[i]);
+    if (sse_type[i] > 3) return sats_fail(SATS_ERR_ARG, "sats_build_structure_from_ca: SSE %d has type %d", i, sse_type[i]);
+    const int rc = sats_fit_axis(sse_type[i], n_res[i], ca_xyz + 3 * at, &dir[3 * (size_t)i], &cen[3 * (size_t)i]);
+    if (rc < 0) return rc;
+    has[(size_t)i] = rc == 0;
+    if (rc == 1) fprintf(stderr, "WARNING: SSE %d has only %d residues, cannot fit axis\n", i, n_res[i]);
+    at += (size_t)n_res[i];
+  }
+  return build_structure_impl(name, n, sse_type, cen.data(), dir.data(), has.data(), out);
 }
 SATS_CATCH_ALL
 

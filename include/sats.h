@@ -101,8 +101,8 @@ int sats_db_write_packed(const sats_db *db, const char *path);
 int sats_db_read_packed(const char *path, sats_db **out);
 
 /* ---- query construction (replaces the pure core of scripts/pytableaucreate.py) -----------------------------
- * The PDB / DSSP front end of the reference's scripts (Bio.PDB, axis fitting) stays outside this library; these three
- * functions turn fitted SSE axes into a searchable structure.
+ * From the C-alpha traces of a protein's secondary-structure elements to a searchable structure, the way the reference's
+ * scripts do it (Kamat & Lesk 2007; Konagurthu, Stuckey & Lesk 2008):
  *   sats_tabcode_from_angle  angle_to_tabcode (scripts/pttableau.py:434-469): omega in (-pi, pi] -> "PE", "OT", ...; every
  *                            interval is half-open on the left; out of range / NaN (ValueError there) -> SATS_ERR_ARG
  *   sats_relative_angle      PTNode.relative_angle (scripts/ptnode.py:752-880) over LineLineIntersect (scripts/geometry.py:
@@ -113,12 +113,22 @@ int sats_db_read_packed(const char *path, sats_db **out);
  *                            3 3-10 helix), centroid / dircos = n x 3 doubles: codes from the pairwise angles ("??" where
  *                            there is none, "PE" with a warning for a NaN angle), midpoint distances rounded through
  *                            "%6.3f" as the writer does (scripts/convdb2.py:225; > 99.9 clamped as
- *                            scripts/pytableaucreate.py:114-116).  The result is a one-structure sats_db, usable as a query. */
+ *                            scripts/pytableaucreate.py:114-116).  The result is a one-structure sats_db, usable as a query.
+ *   sats_fit_axis            PTNodeHelix.fit_axis / PTNodeStrand.fit_axis (scripts/ptnode.py:1113-1292, :1846-1990): the axis
+ *                            of one SSE from its C-alpha trace (n_res x 3 doubles, N- to C-terminus) as a total least squares
+ *                            line through the triple-plane midpoints (helix, sse_type 1..3) or pair midpoints (strand, 0),
+ *                            oriented N -> C; returns 1 where the reference returns None (helix < 3 residues, strand < 2)
+ *   sats_build_structure_from_ca   the two together: n SSEs, n_res[i] residues each, C-alpha coordinates concatenated; an
+ *                            SSE without an axis keeps "??" codes and 0.000 distances, as the reference's None propagates.
+ * What remains outside is the PDB / DSSP front end that decides which residues form which SSE (Bio.PDB, DSSP / STRIDE).     */
 int sats_tabcode_from_angle(double omega, char code[3]);
 int sats_relative_angle(const double c_self[3], const double d_self[3], const double c_other[3],
                         const double d_other[3], double *omega);
 int sats_build_structure(const char *name, int n, const uint8_t *sse_type, const double *centroid,
                          const double *dircos, sats_db **out);
+int sats_fit_axis(int sse_type, int n_res, const double *ca_xyz, double dircos[3], double centroid[3]);
+int sats_build_structure_from_ca(const char *name, int n, const uint8_t *sse_type, const int32_t *n_res,
+                                 const double *ca_xyz, sats_db **out);
 
 /* ---- Gumbel statistics (replaces gumbelstats.h:27-39) ----------------------------------------- */
 extern const double sats_gumbel_a;   /* gumbelstats.h:27 */
