@@ -310,7 +310,7 @@ def ours(args):
     # N > 1: every rank uploads the query and searches its shard; the shards' int32 score vectors are then gathered to
     #        rank 0 over NCCL straight from the searchers' device buffers ("one tiny gather after"), brought into
     #        original db order on the device and copied to the host once -- a step ends with the full 100k-score row on rank 0.
-    gather_ms = nccl_ms = 0.0
+    gather_ms = 0.0
     if dist is None:
         barrier()
         e0 = time.perf_counter()
@@ -368,54 +368,13 @@ def ours(args):
         for _ in range(args.steps):
             gather_ms += step(True)
         barrier()
-        nccl_ms = (time.perf_counter() - e0) * 1e3
+        e2e_ms = (time.perf_counter() - e0) * 1e3
+        d2h_bytes = 4 * DB_SIZE
         if rank == 0:                    # the assembled row must be the unsharded result: spot-check against one local search
             ref_row = np.full((1, len(db)), np.iinfo(np.int32).min, np.int32)
             sr.search(qs, p, scores=ref_row)
             mine = sr.entry_index()
             assert np.array_equal(scores[0, mine], ref_row[0, mine]) and scores.min() > np.iinfo(np.int32).min
-            gathered_row = scores.copy()
-
-        # Variant 2, zero copy: all ranks map ONE shared-memory segment, bind it with sats_search_bind_host_scores(), and the
-        # kernels' arg-max epilogues store every score straight into it, in original db order.  Nothing to gather: a step is
-        # upload + launch + stream sync + one barrier (so that rank 0 knows every rank's stores have landed).
-        from multiprocessing import shared_memory
-        names = [None]
-        if rank == 0:
-            shm = shared_memory.SharedMemory(create=True, size=4 * DB_SIZE)
-            names = [shm.name]
-        dist.broadcast_object_list(names, src=0)
-        if rank != 0:
-            shm = shared_memory.SharedMemory(name=names[0])
-        shared = np.ndarray((1, DB_SIZE), np.int32, buffer=shm.buf)
-        if rank == 0:
-            shared[:] = np.iinfo(np.int32).min
-        barrier()
-        sr.bind_host_scores(shared)
-
-        def zstep():
-            sr.upload(qs)
-            sr.launch(p, 0)
-            sr.sync()
-            dist.barrier()
-
-        zstep()
-        barrier()
-        e0 = time.perf_counter()
-        for _ in range(args.steps):
-            zstep()
-        barrier()
-        e2e_ms = (time.perf_counter() - e0) * 1e3
-        if rank == 0:
-            assert np.array_equal(shared, gathered_row), "zero-copy row differs from the gathered one"
-        d2h_bytes = 4 * DB_SIZE
-        barrier()
-        sr.bind_host_scores(None)
-        del shared
-        shm.close()
-        barrier()
-        if rank == 0:
-            shm.unlink()
     clk = clocks.stop() if rank == 0 else None
 
     rank_ms = [dev_ms / args.steps]
@@ -423,10 +382,10 @@ def ours(args):
         every = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(n_gpus)]
         dist.all_gather(every, torch.tensor([dev_ms / args.steps], device=dev, dtype=torch.float64))
         rank_ms = [float(x) for x in every]            # device-timed ms per step of every rank: the spread is the load imbalance
-        t = torch.tensor([dev_ms, e2e_ms, float(launches), wall_ms, nccl_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([dev_ms, e2e_ms, float(launches), wall_ms], device=dev, dtype=torch.float64)
         mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        dev_ms, e2e_ms, wall_ms, nccl_ms = float(mx[0]), float(mx[1]), float(mx[3]), float(mx[4])
+        dev_ms, e2e_ms, wall_ms = float(mx[0]), float(mx[1]), float(mx[3])
         launches = int(sm[2])
     if rank != 0:
         if dist is not None:
@@ -488,15 +447,11 @@ def ours(args):
         "e2e": {"value": e2e_value, "unit": "structures/s",
                 "h2d_bytes_per_step": int(n_gpus * ((576 + 8 * 19 * 19 + 15) // 16 * 16 + 12)),      # query blob + its offset / size words, per GPU
                 "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_ms / args.steps,
+                "gather_ms_per_step": (gather_ms / args.steps) if n_gpus > 1 else None,
                 "path": "sats_search(): host query in, host scores out" if n_gpus == 1 else
-                        "per rank upload + launch + sync, then one barrier; the kernels store every score straight into ONE "
-                        "shared, page-locked host buffer in original db order (sats_search_bind_host_scores): zero copy, nothing "
-                        "to gather",
-                "nccl_gather_variant": None if n_gpus == 1 else {
-                    "value": DB_SIZE / (nccl_ms / args.steps / 1e3), "ms_per_step": nccl_ms / args.steps,
-                    "gather_ms_per_step": gather_ms / args.steps,
-                    "path": "per rank upload + launch; NCCL all-gather of the shards' device score vectors; rank 0 un-permutes "
-                            "them to original db order on the device and copies the 100k scores to pinned host memory"}},
+                        "per rank upload + launch; NCCL all-gather of the shards' device score vectors; rank 0 un-permutes them "
+                        "to original db order on the device and copies the 100k scores to pinned host memory "
+                        "(gather_ms_per_step = that tail, rank 0)"},
         "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
         "reference_gpu_same_box": ref_gpu,
         "local_entries_rank0": n_local, "rank_ms_per_step": rank_ms,

@@ -69,7 +69,7 @@ def _load() -> C.CDLL:
         "sats_search_upload": (ci, [vp, vp, ci, ci]),
         "sats_search_launch": (ci, [vp, P(Params), C.c_uint32, P(C.c_float)]),
         "sats_search_collect": (ci, [vp, vp, vp]), "sats_searcher_sync": (ci, [vp]),
-        "sats_search_collect_begin": (ci, [vp]), "sats_search_bind_host_scores": (ci, [vp, vp, ci]),
+        "sats_search_collect_begin": (ci, [vp]),
         "sats_search_device_results": (ci, [vp, P(vp), P(ci), P(ci), vp]), "sats_searcher_entry_index": (ci, [vp, vp]),
         "sats_searcher_launch_count": (C.c_longlong, [vp]),
         "sats_searcher_get_xorwow": (ci, [vp, vp]), "sats_searcher_reset_xorwow": (ci, [vp, C.c_uint64]),
@@ -397,17 +397,6 @@ class Searcher:
 
     def sync(self):
         _check(lib().sats_searcher_sync(self._h))
-
-    def bind_host_scores(self, scores: np.ndarray | None):
-        """Zero-copy results: every launch from now on stores its scores straight into `scores` (int32 [qcap, len(db)], original
-        db order) from the kernel; complete after sync().  None unbinds.  The array must stay alive while bound."""
-        if scores is None:
-            _check(lib().sats_search_bind_host_scores(self._h, None, 0))
-            self._bound = None
-            return
-        _out_array(scores, (scores.shape[0], self.count), "scores")
-        _check(lib().sats_search_bind_host_scores(self._h, scores.ctypes.data, scores.shape[0]))
-        self._bound = scores
 
     def collect_begin(self):
         _check(lib().sats_search_collect_begin(self._h))

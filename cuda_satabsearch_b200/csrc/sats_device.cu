@@ -190,9 +190,6 @@ struct sats_searcher {
   int4 *d_stream_list = nullptr; size_t stream_list_cap = 0;
   int4 *h_stream = nullptr; size_t h_stream_cap = 0;
   bool stream_valid = false;              // the last launch ran with the cut bound
-  // zero-copy results: the caller's page-locked host buffer and its device alias (sats_search_bind_host_scores)
-  int32_t *bound_host = nullptr, *bound_dev = nullptr;
-  int bound_qcap = 0;
   long long launches = 0;
   std::set<kernel_fn> smem_opted;         // kernel variants already opted into 227 KB of dynamic shared memory
 };
@@ -384,7 +381,6 @@ extern "C" void sats_searcher_free(sats_searcher *s)
   cudaFree(s->d_scores); cudaFree(s->d_maps); cudaFree(s->d_topk); cudaFreeHost(s->h_topk);
   cudaFree(s->d_sorted_order); cudaFree(s->d_hits); cudaFreeHost(s->h_hits);
   cudaFree(s->d_stream_thr); cudaFree(s->d_stream_cursor); cudaFree(s->d_stream_list); cudaFreeHost(s->h_stream);
-  if (s->bound_host) cudaHostUnregister(s->bound_host);
   if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
   cudaFreeHost(s->h_qstage); cudaFreeHost(s->h_scores); cudaFreeHost(s->h_maps);
   if (s->ev0) cudaEventDestroy(s->ev0);
@@ -597,7 +593,7 @@ try {
   memcpy(&key.p, pp, sizeof key.p);       // (struct copy would leave padding bytes undefined)
   key.qbase = query_index_base; key.q = Q; key.d = D; key.qsig = s->qsig;
   const void *key_ptrs[10] = {s->d_qblobs, s->d_qoff, s->d_qbytes, s->d_scores, pp->lsoln ? (const void *)s->d_maps : nullptr, hit_thr,
-                              s->d_stream_list, s->d_counters, (const void *)(uintptr_t)s->stream_list_cap, s->bound_dev};
+                              s->d_stream_cursor, s->d_stream_list, s->d_counters, (const void *)(uintptr_t)s->stream_list_cap};
   memcpy(key.ptr, key_ptrs, sizeof key.ptr);
   static const bool no_graph_fast = getenv("SATS_NO_GRAPH") != nullptr || getenv("SATS_TW") != nullptr || getenv("SATS_TEAMS") != nullptr;
   if (!xorwow && !no_graph_fast && s->graph_exec && s->graph_key_valid && memcmp(&key, &s->graph_key, sizeof key) == 0) {
@@ -635,9 +631,6 @@ try {
   k.temps = reinterpret_cast<const float *>(s->d_accept + (size_t)SATS_K_MOVES * (SATS_K_DCLAMP + 1));
   k.out_scores = s->d_scores; k.out_maps = pp->lsoln ? s->d_maps : nullptr; k.out_stride = std::max(1, D);
   k.xw_states = s->d_xw; k.pool_list = s->d_pool_list; k.xw_blocks = s->d_xw_blocks;
-  if (s->bound_dev && Q > s->bound_qcap)
-    return sats_fail(SATS_ERR_ARG, "%d queries uploaded but the bound host score buffer holds %d rows", Q, s->bound_qcap);
-  k.host_scores = s->bound_dev; k.host_stride = s->db_count;
   k.hit_thr = hit_thr; k.hit_cursor = s->d_stream_cursor; k.hit_list = s->d_stream_list; k.hit_cap = (unsigned)s->stream_list_cap;
 
   if (r1 > r0) {
@@ -837,7 +830,7 @@ try {
           s->graph_counters = ncounters;
         }
         CK(cudaGraphLaunch(s->graph_exec, s->stream));
-        key.ptr[7] = s->d_counters;          // may have been (re)allocated above
+        key.ptr[8] = s->d_counters;          // may have been (re)allocated above
         memcpy(&s->graph_key, &key, sizeof key);      // byte copy: the comparison above is a memcmp, padding included
         s->graph_key_valid = true;
       }
@@ -1160,34 +1153,6 @@ try {
   return SATS_OK;
 }
 SATS_CATCH_ALL
-
-// ---- zero-copy results ----------------------------------------------------------------------------------------------------
-extern "C" int sats_search_bind_host_scores(sats_searcher *s, int32_t *scores, int qcap)
-{
-  if (!s || (scores && qcap < 1)) return sats_fail(SATS_ERR_ARG, "sats_search_bind_host_scores: bad argument");
-  CK(cudaSetDevice(s->device));
-  CK(cudaStreamSynchronize(s->stream));
-  if (s->bound_host) {
-    cudaHostUnregister(s->bound_host);
-    s->bound_host = s->bound_dev = nullptr;
-    s->bound_qcap = 0;
-  }
-  if (!scores) return SATS_OK;
-  const size_t bytes = (size_t)qcap * std::max(1, s->db_count) * sizeof(int32_t);
-  cudaError_t e = cudaHostRegister(scores, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
-  if (e == cudaErrorHostMemoryAlreadyRegistered) {       // another searcher of this process bound the same buffer: share it
-    cudaGetLastError();
-    e = cudaSuccess;
-  } else if (e == cudaSuccess) {
-    s->bound_host = scores;                               // this searcher owns the registration
-  }
-  CK(e);
-  void *dev = nullptr;
-  CK(cudaHostGetDevicePointer(&dev, scores, 0));
-  s->bound_dev = static_cast<int32_t *>(dev);
-  s->bound_qcap = qcap;
-  return SATS_OK;
-}
 
 // ---- streaming hits (second half) ----------------------------------------------------------------------
 extern "C" int sats_search_bind_cut(sats_searcher *s, double z_min)

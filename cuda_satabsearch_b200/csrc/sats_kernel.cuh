@@ -644,8 +644,6 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
   const unsigned team_tag = ~(uint32_t)key;
   if (tl == 0) {
     p.out_scores[(size_t)out_slot * p.out_stride + entry_sorted] = team_best;
-    if (p.host_scores != nullptr)      // zero-copy: the result lands in the caller's (mapped) host buffer, original order
-      p.host_scores[(size_t)(query_index - p.q_index_base) * p.host_stride + entry_orig] = team_best;
     if (p.hit_thr != nullptr && team_best >= __ldg(p.hit_thr + out_slot * (SATS_MAXDIM_EXT + 1) + v.n2)) {
       const unsigned pos = atomicAdd(p.hit_cursor, 1u);
       if (pos < p.hit_cap) p.hit_list[pos] = make_int4(out_slot, entry_sorted, team_best, 0);

@@ -59,10 +59,6 @@ struct SatsKParams {
   unsigned *hit_cursor;            // hits appended so far (may run past hit_cap: the overflow is detected on the host)
   int4 *hit_list;                  // (query slot, sorted entry index, score, 0)
   unsigned hit_cap;
-  // zero-copy results (sats_search_bind_host_scores): a page-locked, device-mapped HOST buffer indexed [query position in the
-  // batch][ORIGINAL entry index]; when bound, the arg-max epilogue also stores every score straight into it
-  int32_t *host_scores;            // nullptr = not bound
-  int host_stride;                 // entries of the whole database
   // outputs, indexed [query slot][sorted entry index]
   int32_t *out_scores;
   int8_t *out_maps;                // rows of SATS_K_MAPROW bytes, or nullptr

@@ -258,14 +258,6 @@ int sats_search_collect(sats_searcher *s, int32_t *scores, int32_t *maps);
 /* Multi-GPU hosts: sats_search_collect_begin() only ENQUEUES the device -> host copies (pinned staging), so that every
  * GPU's copy is in flight before the first sats_search_collect() waits; collect without begin does both.             */
 int sats_search_collect_begin(sats_searcher *s);
-/* Zero-copy results: bind a caller buffer of qcap x sats_db_count(db) int32 (rows = queries in batch order, columns =
- * ORIGINAL db index: the layout of sats_search()'s `scores`).  The library page-locks and maps it (cudaHostRegister) and from
- * then on every launch ALSO stores each entry's best score straight into it from the kernel's arg-max epilogue; the buffer is
- * complete after sats_searcher_sync().  No device -> host copy, no host-side scatter, nothing to gather: all searchers of a
- * multi-GPU run -- shards in one process, or ranks of a multi-process run that map one shared-memory segment -- bind the same
- * memory and each fills the entries it owns (entries outside a launch's pool stay untouched).  scores = NULL unbinds; the
- * buffer must stay valid while bound.  Maps (LSOLN) still travel through sats_search_collect().                             */
-int sats_search_bind_host_scores(sats_searcher *s, int32_t *scores, int qcap);
 /* SURVEY 8(e) "one tiny gather after": the results where they are, for callers that gather the shards with their own
  * collective (ncclGather / AllGather) instead of N host copies.  *d_scores = device pointer to int32 [qcount][entries]
  * in DEVICE order (row = query slot, column = position in this searcher's decreasing-size order; entries outside the

@@ -162,48 +162,3 @@ def test_device_results_and_overlapped_collect(fixtures):
     assert np.array_equal(merged, want) and np.array_equal(via_device, want)
     for sr in shards:
         sr.close()
-
-
-def test_zero_copy_host_scores(fixtures):
-    """sats_search_bind_host_scores: the kernels store every score straight into one page-locked host buffer in original db
-    order.  Three shards bind the same buffer and fill it between them; a pool-restricted launch leaves the other pool's
-    entries untouched; a batch larger than the bound rows is refused; unbinding stops the stores."""
-    ents = fixtures["small586"][:220]
-    qs = [fixtures["queries_by_name"][n] for n in ("D2PHLB1", "D1UBIA_", "SHEETBC")]
-    db = S.Database.from_structures([s.name for s in ents], [s.tab for s in ents], [s.dmat for s in ents])
-    q = S.Database.from_structures([s.name for s in qs], [s.tab for s in qs], [s.dmat for s in qs])
-    p = S.default_params(lorder=1, lsoln=0, restarts=64, seed=21)
-    whole = S.Searcher(db, 0)
-    want, _ = whole.search(q, p)
-    buf = np.full((3, len(ents)), -5, np.int32)
-    shards = [S.Searcher(db, 0, r, 3) for r in range(3)]
-    for sr in shards:
-        sr.bind_host_scores(buf)
-        sr.upload(q)
-        sr.launch(p, 0)
-    for sr in shards:
-        sr.sync()
-    assert np.array_equal(buf, want)
-    # pool-restricted: only the large pool (threshold 32) is rewritten
-    buf[:] = -5
-    pl = S.default_params(lorder=1, lsoln=0, restarts=64, seed=21, pool=S.POOL_LARGE, pool_threshold=32)
-    for sr in shards:
-        sr.launch(pl, 0)
-    for sr in shards:
-        sr.sync()
-    large = np.array([s.n > 32 for s in ents])
-    assert large.any() and np.array_equal(buf[:, large], want[:, large]) and (buf[:, ~large] == -5).all()
-    # too many queries for the bound rows
-    small = np.zeros((2, len(ents)), np.int32)
-    whole.bind_host_scores(small)
-    whole.upload(q)
-    with pytest.raises(S.SatsError, match="holds 2 rows"):
-        whole.launch(p, 0)
-    whole.bind_host_scores(None)
-    whole.launch(p, 0)
-    whole.sync()
-    assert (small == 0).all()
-    for sr in shards:
-        sr.bind_host_scores(None)
-        sr.close()
-    whole.close()
