@@ -7,7 +7,7 @@ bash profiles/tools/capture.sh $tag > $out/${tag}_capture.log 2>&1
 python profiles/tools/summarize.py launches $out/${tag}_launches.csv > $out/${tag}_launches.txt
 python profiles/tools/summarize.py raw $out/prof_${tag}.ncu-rep > $out/${tag}_kernels.txt
 python profiles/tools/summarize.py source $out/prof_${tag}.ncu-rep 3 > $out/${tag}_source_k3.txt
-python profiles/tools/make_latest.py $out/prof_${tag}.ncu-rep "profiles/${tag}_* (ncu --set full, bench.py --steps 2 --warmup 3 --no-cpu, one B200, 4 launches = one step)" > $out/${tag}_latest.json
+python profiles/tools/make_latest.py $out/prof_${tag}.ncu-rep "profiles/${tag}_* (ncu --set full, bench.py --steps 2 --warmup 3 --no-cpu, one B200, 3 launches = one step)" 1.28e9 3 > $out/${tag}_latest.json
 ncu -i $out/prof_${tag}.ncu-rep --page raw --csv > $out/${tag}_raw.csv 2>/dev/null
 rm -f $out/prof_${tag}.ncu-rep
 for cfg in "sheetbc SHEETBC 165" "n101 d1twfa_ 0" "ubia D1UBIA_ 69"; do

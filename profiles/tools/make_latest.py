@@ -13,8 +13,14 @@ from pathlib import Path
 
 rep, capture = sys.argv[1], sys.argv[2]
 moves = float(sys.argv[3]) if len(sys.argv) > 3 else 100000 * 128 * 100.0
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+keep = int(sys.argv[4]) if len(sys.argv) > 4 else None          # launches of ONE step (the first `keep` captured ones)
+if rep.endswith(".csv"):                                         # an `ncu --page raw --csv` export instead of the report itself
+    out = open(rep).read()
+else:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
+if keep:
+    rows = rows[:2 + keep]
 h = {n: i for i, n in enumerate(rows[0])}
 units = rows[1]
 
