@@ -74,6 +74,23 @@ def test_cli_equals_reference_gpu_binary_with_a_large_pool(tmp_path, fixtures):
         assert rows(ours.stdout) == rows(ref.stdout), g
 
 
+@pytest.mark.skipif(not REF_BIN.exists(), reason="reference binary not built")
+def test_cli_equals_reference_gpu_binary_at_astral_scale(tmp_path, fixtures):
+    """BASELINE configs[1] against the real thing: D1UBIA_ vs the synthetic ASTRAL-scale db (14 297 structures, size-sorted),
+    validation streams, LSOLN = T -- stdout of the drop-in binary must be byte-identical to the stdout of the unmodified
+    reference GPU binary run on the same B200 (every block of the reference grid walks 112 entries here, so the streams'
+    carry-over from entry to entry is exercised 14 169 times)."""
+    base = S.Database.read_packed(REPO / "tests" / "golden" / "small586.satsdb")
+    db = base.bootstrap(14297, 20240501, True)
+    db.write_ascii(tmp_path / "db.ascii")
+    write_query_input(tmp_path / "q.input", "db.ascii", True, True, [fixtures["queries_by_name"]["D1UBIA_"]])
+    ref = run([REF_BIN, "-r", 128], tmp_path / "q.input", tmp_path)
+    assert ref.returncode == 0, ref.stderr.decode()[-1500:]
+    ours = run([CLI, "-r", 128, "-R", "xorwow", "-A", "fast"], tmp_path / "q.input", tmp_path)
+    assert ours.returncode == 0, ours.stderr.decode()[-1500:]
+    assert ours.stdout == ref.stdout and ours.stdout.count(b"\n") > 14297 + 3
+
+
 def test_cli_production_mode_equals_oracle_rendering(tmp_path, fixtures, oracle):
     """Philox mode, db with both pools (threshold 96 -> plant two large structures), two queries, LSOLN=T."""
     ents = list(fixtures["small586"][:150])
