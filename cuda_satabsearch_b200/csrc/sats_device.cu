@@ -187,8 +187,8 @@ struct sats_searcher {
   bool cut_bound = false; double cut_z = 0.0;
   int32_t *d_stream_thr = nullptr; size_t stream_thr_cap = 0;      // [query slot][SATS_MAXDIM_EXT + 1]
   unsigned *d_stream_cursor = nullptr;
-  int4 *d_stream_list = nullptr; size_t stream_list_cap = 0;
-  int4 *h_stream = nullptr; size_t h_stream_cap = 0;
+  int2 *d_stream_list = nullptr; size_t stream_list_cap = 0;
+  int2 *h_stream = nullptr; size_t h_stream_cap = 0;
   bool stream_valid = false;              // the last launch ran with the cut bound
   long long launches = 0;
   std::set<kernel_fn> smem_opted;         // kernel variants already opted into 227 KB of dynamic shared memory
@@ -560,8 +560,9 @@ try {
   s->stream_valid = false;
   const int32_t *hit_thr = nullptr;
   if (s->cut_bound) {
+    if (Q > 65536) return sats_fail(SATS_ERR_ARG, "streaming hits: at most 65536 queries per batch (a hit record keeps the query slot in 16 bits)");
     // one integer score threshold per (query slot, structure order), as in sats_search_hits(); list room for every
-    // (query, entry) pair up to 4 M hits (64 MB) -- beyond that the reader falls back to the dense post-pass
+    // (query, entry) pair up to 4 M hits (32 MB) -- beyond that the reader falls back to the dense post-pass
     const int T = SATS_MAXDIM_EXT + 1;
     std::vector<int32_t> thr((size_t)Q * T);
     for (int q = 0; q < Q; q++)
@@ -574,7 +575,7 @@ try {
     const size_t want = std::min<size_t>((size_t)Q * std::max(1, D), (size_t)4 << 20);
     if (want > s->stream_list_cap) {
       cudaFree(s->d_stream_list); s->d_stream_list = nullptr; s->stream_list_cap = 0;
-      CK(cudaMalloc(&s->d_stream_list, want * sizeof(int4)));
+      CK(cudaMalloc(&s->d_stream_list, want * sizeof(int2)));
       s->stream_list_cap = want;
     }
     if (!s->d_stream_cursor) CK(cudaMalloc(&s->d_stream_cursor, sizeof(unsigned)));
@@ -1181,21 +1182,22 @@ try {
   }
   if ((size_t)total > s->h_stream_cap) {
     cudaFreeHost(s->h_stream); s->h_stream = nullptr; s->h_stream_cap = 0;
-    CK(cudaMallocHost(&s->h_stream, (size_t)total * sizeof(int4)));
+    CK(cudaMallocHost(&s->h_stream, (size_t)total * sizeof(int2)));
     s->h_stream_cap = total;
   }
   if (total) {
-    CK(cudaMemcpyAsync(s->h_stream, s->d_stream_list, (size_t)total * sizeof(int4), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(s->h_stream, s->d_stream_list, (size_t)total * sizeof(int2), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
-    if (d2h_bytes) *d2h_bytes += (int64_t)total * (int64_t)sizeof(int4);
+    if (d2h_bytes) *d2h_bytes += (int64_t)total * (int64_t)sizeof(int2);
   }
   // the kernel appends in completion order: bring every query's hits into device order (decreasing structure order, then
   // file order) -- the order sats_search_hits() and the -z printer use
   std::vector<std::vector<std::pair<int32_t, int32_t>>> per((size_t)Q);
   for (unsigned k = 0; k < total; k++) {
-    const int4 h = s->h_stream[k];
-    if (h.x < 0 || h.x >= Q) return sats_fail(SATS_ERR_CUDA, "corrupt hit record");
-    per[(size_t)h.x].emplace_back(h.y, h.z);
+    const int2 h = s->h_stream[k];
+    const int slot = (int)((uint32_t)h.y & 0xffffu), score = h.y >> 16;          // arithmetic shift: the score is signed
+    if (slot >= Q) return sats_fail(SATS_ERR_CUDA, "corrupt hit record");
+    per[(size_t)slot].emplace_back(h.x, score);
   }
   for (int q = 0; q < Q; q++) {
     auto &v = per[(size_t)q];

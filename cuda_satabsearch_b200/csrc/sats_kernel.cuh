@@ -646,7 +646,7 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
     p.out_scores[(size_t)out_slot * p.out_stride + entry_sorted] = team_best;
     if (p.hit_thr != nullptr && team_best >= __ldg(p.hit_thr + out_slot * (SATS_MAXDIM_EXT + 1) + v.n2)) {
       const unsigned pos = atomicAdd(p.hit_cursor, 1u);
-      if (pos < p.hit_cap) p.hit_list[pos] = make_int4(out_slot, entry_sorted, team_best, 0);
+      if (pos < p.hit_cap) p.hit_list[pos] = make_int2(entry_sorted, (int)(((uint32_t)team_best << 16) | (uint32_t)out_slot));
     }
   }
   if (LSOLN && best == team_best && (unsigned)best_tag == team_tag) {

@@ -57,7 +57,7 @@ struct SatsKParams {
   // score reaches hit_thr[query slot][entry order] to one device list, so that only the hits ever travel to the host
   const int32_t *hit_thr;          // [query slot][SATS_MAXDIM_EXT + 1], nullptr = no cut bound
   unsigned *hit_cursor;            // hits appended so far (may run past hit_cap: the overflow is detected on the host)
-  int4 *hit_list;                  // (query slot, sorted entry index, score, 0)
+  int2 *hit_list;                  // (sorted entry index, score << 16 | query slot): |score| <= 12210 and slot < 65536 (gridDim.y)
   unsigned hit_cap;
   // outputs, indexed [query slot][sorted entry index]
   int32_t *out_scores;

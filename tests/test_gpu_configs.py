@@ -256,7 +256,7 @@ def test_streamed_hits_equal_the_dense_post_pass(base, fixtures):
             cnt, idx, sc, nbytes = sr.streamed_hits(cap)
             want = sr.hits(z_min, cap)
             assert np.array_equal(cnt, want[0]) and np.array_equal(idx, want[1]) and np.array_equal(sc, want[2]), (shard, z_min)
-            assert nbytes == 4 + 16 * int(cnt.sum())                    # the counter and one 16-byte record per hit
+            assert nbytes == 4 + 8 * int(cnt.sum())                     # the counter and one 8-byte record per hit
             if z_min >= 1.0:
                 assert nbytes < 0.05 * 4 * len(qs) * sr.entries           # a few per cent of the dense score matrix
         sr.bind_cut(None)
