@@ -212,3 +212,26 @@ def test_cli_hit_modes_are_shard_invariant(tmp_path, fixtures):
         three = run([CLI, "-r", 64, "-g", 3] + extra, tmp_path / "q.input", tmp_path)
         assert one.returncode == 0 and three.returncode == 0, three.stderr.decode()[-1000:]
         assert one.stdout == three.stdout and len(one.stdout) > 1000, extra
+
+
+def test_results_do_not_depend_on_the_launch_plan(tmp_path, fixtures):
+    """Production chains are keyed by (seed, query, original entry index, restart) only, so the launch plan must not show in the
+    results: one launch per size class instead of merged work queues (SATS_NO_MERGE), kernel-by-kernel launches instead of the
+    replayed CUDA graph (SATS_NO_GRAPH), narrower teams (SATS_TW), fewer teams per CTA (SATS_TEAMS) -- byte-identical stdout."""
+    ents = fixtures["small586"]
+    qs = [fixtures["queries_by_name"][n] for n in ("D2PHLB1", "SHEETBC", "d1twfa_")]
+    write_ascii_db(tmp_path / "db.ascii", ents)
+    write_query_input(tmp_path / "q.input", "db.ascii", True, True, qs)
+
+    def out(env):
+        e = dict(os.environ)
+        e.update(env)
+        with open(tmp_path / "q.input", "rb") as fh:
+            p = subprocess.run([str(CLI), "-r", "96"], stdin=fh, cwd=tmp_path, capture_output=True, timeout=600, env=e)
+        assert p.returncode == 0, p.stderr.decode()[-1000:]
+        return p.stdout
+
+    want = out({})
+    assert len(want) > 50000
+    for env in ({"SATS_NO_MERGE": "1"}, {"SATS_NO_GRAPH": "1"}, {"SATS_TW": "32"}, {"SATS_TW": "64", "SATS_TEAMS": "2"}):
+        assert out(env) == want, env
