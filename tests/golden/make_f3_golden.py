@@ -270,7 +270,7 @@ def main():
         rows.append("".join(cells))
     from_ca = {"name": "f3trac", "types": ca_types, "traces": [t.tolist() for t in traces], "ascii": "\n".join(rows) + "\n"}
     OUT.write_text(json.dumps({"generator": "tests/golden/make_f3_golden.py", "codes": codes, "pairs": pairs,
-                               "structure": structure, "axes": axes, "from_ca": from_ca}, indent=0))
+                               "structure": structure, "axes": axes, "from_ca": from_ca}, separators=(",", ":")))
     print("wrote", OUT, len(codes), "angles,", len(pairs), "axis pairs,", len(axes), "fitted axes")
 
 

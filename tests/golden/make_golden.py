@@ -127,7 +127,7 @@ def main():
         "input": "d2phlb1.input", "db": "small586", "dbfile": DBS["small586"], "lorder": True, "lsoln": False,
         "restarts": 4096, "pool_threshold": 32, "stdout_md5": md5(raw), "blocks": blocks,
     }
-    (HERE / "golden.json").write_text(json.dumps(out, indent=0, separators=(",", ":")) + "\n")
+    (HERE / "golden.json").write_text(json.dumps(out, separators=(",", ":")) + "\n")
     print("wrote", HERE / "golden.json")
 
 
