@@ -18,6 +18,7 @@
 #include <memory>
 #include <new>
 #include <numeric>
+#include <thread>
 #include <strings.h>
 
 #include "sats_internal.h"
@@ -149,7 +150,9 @@ bool read_header(Cursor &c, char name[9], int *order)
 }
 
 // Parses consecutive entries until the text ends or a header fails to parse.
-int parse_entries(Cursor &c, const char *what, sats_db *db, int max_order = SATS_MAXDIM)
+// `warn` (parallel parsing): collect the oversize warnings instead of printing them, and leave the summary line to the caller
+int parse_entries(Cursor &c, const char *what, sats_db *db, int max_order = SATS_MAXDIM, std::string *warn = nullptr,
+                  int *skipped_out = nullptr)
 {
   std::vector<uint8_t> ttab;
   std::vector<float> tdm;
@@ -160,8 +163,11 @@ int parse_entries(Cursor &c, const char *what, sats_db *db, int max_order = SATS
     if (n < 1) return sats_fail(SATS_ERR_PARSE, "%s structure %s has bad order %d", what, name, n);
     bool keep = n <= max_order;
     if (!keep) {
-      fprintf(stderr, "Tableau %s order %d is too large (max is %d)\n", name, n, max_order);
-      fprintf(stderr, "WARNING: excluded %s structure %s as it is too large\n", what, name);
+      char msg[256];
+      int m = snprintf(msg, sizeof msg, "Tableau %s order %d is too large (max is %d)\nWARNING: excluded %s structure %s as it is too large\n",
+                       name, n, max_order, what, name);
+      if (warn) warn->append(msg, (size_t)m);
+      else fputs(msg, stderr);
       skipped++;
     }
     size_t cells = (size_t)n * (n + 1) / 2;
@@ -205,8 +211,79 @@ int parse_entries(Cursor &c, const char *what, sats_db *db, int max_order = SATS
     }
     if (keep) db->append(name, n, ttab.data(), tdm.data());
   }
-  if (skipped) fprintf(stderr, "WARNING: skipped %d %s tableaux of order > %d\n", skipped, what, max_order);
+  if (skipped_out) *skipped_out = skipped;
+  else if (skipped) fprintf(stderr, "WARNING: skipped %d %s tableaux of order > %d\n", skipped, what, max_order);
   return 0;
+}
+
+// A large database text parsed on several threads: entries are independent, and in the writer's format a blank line separates
+// them, so the text is cut at blank lines near the even split points and every piece goes through parse_entries() on its own.
+// Returns false -- and the caller parses serially, which also reproduces the serial error message -- whenever anything is
+// not plainly regular: no blank-line boundary near a split point, a piece that fails or stops before its end.
+bool parse_entries_parallel(const char *text, size_t len, int max_order, sats_db *db)
+{
+  size_t want = 8;
+  if (const char *e = getenv("SATS_PARSE_THREADS")) want = (size_t)std::max(1, atoi(e));
+  const size_t threads = std::min<size_t>(want, std::max(1u, std::thread::hardware_concurrency()));
+  if (threads < 2 || len < (size_t)(4u << 20)) return false;
+  std::vector<size_t> cut(1, 0);
+  for (size_t t = 1; t < threads; t++) {
+    size_t pos = std::max(cut.back(), len / threads * t);
+    const char *hit = nullptr;
+    for (const char *q = text + pos; q + 1 < text + len; q++)
+      if (q[0] == '\n' && q[1] == '\n') { hit = q + 2; break; }
+    if (!hit) break;
+    // the piece must start like a header: a name, an integer, end of line
+    const char *q = hit;
+    while (q < text + len && *q != '\n' && !isspace((unsigned char)*q)) q++;
+    if (q == hit) return false;
+    while (q < text + len && (*q == ' ' || *q == '\t')) q++;
+    const char *num = q;
+    while (q < text + len && *q >= '0' && *q <= '9') q++;
+    if (q == num) return false;
+    while (q < text + len && (*q == ' ' || *q == '\t' || *q == '\r')) q++;
+    if (q < text + len && *q != '\n') return false;
+    if ((size_t)(hit - text) > cut.back()) cut.push_back((size_t)(hit - text));
+  }
+  cut.push_back(len);
+  const size_t pieces = cut.size() - 1;
+  if (pieces < 2) return false;
+  struct Piece { sats_db db; std::string warn; int skipped = 0, rc = 0; bool complete = false; };
+  std::vector<Piece> out(pieces);
+  {
+    std::vector<std::thread> pool;
+    struct Join { std::vector<std::thread> &p; ~Join() { for (auto &t : p) if (t.joinable()) t.join(); } } join{pool};
+    auto work = [&](size_t k) {
+      Piece &pc = out[k];
+      try {
+        pc.db.tri_off.push_back(0);
+        Cursor c{text + cut[k], text + cut[k + 1]};
+        pc.rc = parse_entries(c, "database", &pc.db, max_order, &pc.warn, &pc.skipped);
+        c.skip_space();
+        pc.complete = pc.rc == 0 && c.eof();
+      } catch (...) { pc.rc = SATS_ERR_NOMEM; }
+    };
+    for (size_t k = 1; k < pieces; k++) pool.emplace_back(work, k);
+    work(0);
+  }
+  for (const Piece &pc : out) if (!pc.complete) return false;
+  int skipped = 0;
+  size_t n_entries = 0, n_cells = 0;
+  for (const Piece &pc : out) { n_entries += pc.db.order.size(); n_cells += pc.db.tab.size(); }
+  db->order.reserve(n_entries); db->names.reserve(9 * n_entries); db->tri_off.reserve(n_entries + 1);
+  db->tab.reserve(n_cells); db->dmat.reserve(n_cells);
+  for (Piece &pc : out) {
+    fputs(pc.warn.c_str(), stderr);
+    skipped += pc.skipped;
+    const int64_t base = db->tri_off.back();
+    db->order.insert(db->order.end(), pc.db.order.begin(), pc.db.order.end());
+    db->names.insert(db->names.end(), pc.db.names.begin(), pc.db.names.end());
+    db->tab.insert(db->tab.end(), pc.db.tab.begin(), pc.db.tab.end());
+    db->dmat.insert(db->dmat.end(), pc.db.dmat.begin(), pc.db.dmat.end());
+    for (size_t e = 1; e < pc.db.tri_off.size(); e++) db->tri_off.push_back(base + pc.db.tri_off[e]);
+  }
+  if (skipped) fprintf(stderr, "WARNING: skipped %d %s tableaux of order > %d\n", skipped, "database", max_order);
+  return true;
 }
 
 // a structure handed over as arrays or read from the packed cache must use the same alphabet the ASCII parser enforces:
@@ -227,6 +304,17 @@ int slurp(const char *path, std::string *out)
 {
   FILE *fp = fopen(path, "rb");
   if (!fp) return sats_fail(SATS_ERR_IO, "ERROR opening db file %s", path);
+  // regular file: one allocation, one read; anything else (pipe, /proc): chunked
+  if (fseek(fp, 0, SEEK_END) == 0) {
+    const long size = ftell(fp);
+    if (size > 0 && fseek(fp, 0, SEEK_SET) == 0) {
+      out->resize((size_t)size);
+      const size_t got = fread(&(*out)[0], 1, (size_t)size, fp);
+      out->resize(got);
+    } else {
+      rewind(fp);
+    }
+  }
   char buf[1 << 16];
   size_t n;
   while ((n = fread(buf, 1, sizeof buf, fp)) > 0) out->append(buf, n);
@@ -242,9 +330,13 @@ try {
   if (max_order < 1 || max_order > SATS_MAXDIM_EXT) return sats_fail(SATS_ERR_ARG, "max_order %d outside 1..%d", max_order, SATS_MAXDIM_EXT);
   std::unique_ptr<sats_db> db(new sats_db());
   db->tri_off.push_back(0);
-  Cursor c{text, text + len};
-  int rc = parse_entries(c, "database", db.get(), max_order);
-  if (rc) return rc;
+  if (!parse_entries_parallel(text, len, max_order, db.get())) {
+    db.reset(new sats_db());
+    db->tri_off.push_back(0);
+    Cursor c{text, text + len};
+    int rc = parse_entries(c, "database", db.get(), max_order);
+    if (rc) return rc;
+  }
   *out = db.release();
   return SATS_OK;
 }

@@ -4,6 +4,7 @@ the reference's host code.  No search is run here (that needs a GPU and must fai
 import hashlib
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -302,3 +303,48 @@ def test_result_printer_tail_cache_is_transparent():
     for k in list(range(0, len(db), 7)) + [len(db) - 1]:
         n2s, z, p = stats(int(sc[k]), 23, int(orders[k]))
         assert rows[3 + k] == "%-8s %d %g %g %g" % (db.name(k), int(sc[k]), n2s, z, p), k
+
+
+def test_parallel_ascii_parse_equals_serial(tmp_path):
+    """Database texts above 4 MB are cut at blank lines and parsed on several threads; the result -- structures, their order,
+    the oversize warnings and their order -- must be what the serial parse gives, and anything irregular (here: a piece
+    that fails) must fall back to the serial parse and its error message."""
+    import os
+    base = S.Database.read_packed(GOLDEN / "small586.satsdb")
+    db = base.bootstrap(9000, 77, False)
+    path = tmp_path / "db.ascii"
+    db.write_ascii(path)
+    text = path.read_text()
+    assert len(text) > 8 << 20
+    # plant oversize entries (order 112 > 111) at a few places: they are skipped with warnings, in file order
+    big = "toobig1  112\n" + "\n".join(" ".join(["e "] * (i + 1)) + " " for i in range(112)) + "\n" + \
+          "\n".join(" ".join(["%6.3f" % 1.0] * (i + 1)) + " " for i in range(112)) + "\n"
+    entries = text.split("\n\n")
+    for k, at in enumerate((10, 4000, 8990)):
+        entries.insert(at + k, big.replace("toobig1", "toobig%d" % k).rstrip("\n"))
+    text = "\n\n".join(entries)
+    (tmp_path / "w.ascii").write_text(text)
+    code = ("import sys; sys.path.insert(0, %r); import cuda_satabsearch_b200 as S; d = S.Database.read_ascii(%r); "
+            "d.write_packed(%r)")
+    outs = {}
+    for thr in ("1", "6"):
+        env = dict(os.environ, SATS_PARSE_THREADS=thr)
+        p = subprocess.run([sys.executable, "-c", code % (str(REPO), str(tmp_path / "w.ascii"), str(tmp_path / ("p%s.satsdb" % thr)))],
+                           capture_output=True, text=True, env=env, timeout=300)
+        assert p.returncode == 0, p.stderr[-500:]
+        outs[thr] = (hashlib.md5((tmp_path / ("p%s.satsdb" % thr)).read_bytes()).hexdigest(), p.stderr)
+    assert outs["1"] == outs["6"]
+    assert outs["1"][1].count("is too large") == 6 and "skipped 3 database tableaux" in outs["1"][1]
+    assert outs["1"][1].index("toobig0") < outs["1"][1].index("toobig1") < outs["1"][1].index("toobig2")
+    # a broken entry in the middle: same error either way
+    bad = text.replace("toobig1  112", "toobig1  112x", 1)
+    msgs = []
+    for thr in ("1", "6"):
+        os.environ["SATS_PARSE_THREADS"] = thr
+        try:
+            n = len(S.Database.parse_ascii(bad))
+            msgs.append("parsed %d" % n)
+        except S.SatsError as exc:
+            msgs.append(str(exc))
+    os.environ.pop("SATS_PARSE_THREADS", None)
+    assert msgs[0] == msgs[1], msgs
