@@ -108,6 +108,14 @@ __device__ __forceinline__ uint32_t below(int x)
   return ~r;
 }
 
+// the same for x >= 0: no clamp needed
+__device__ __forceinline__ uint32_t below_nonneg(int x)
+{
+  uint32_t r;
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(0xffffffffu), "r"((uint32_t)x));
+  return ~r;
+}
+
 // index of the highest set bit (x != 0): one FLO
 __device__ __forceinline__ int top_bit(uint32_t x)
 {
@@ -494,7 +502,8 @@ struct Chain {
       from = was_mapped ? lo : -1;
       if (W1 <= 2) {
         // word maps: a sentinel bit "SSE n1" above the last one (their masks always have room for it) whose map element
-        // holds "unmapped", so the upper neighbour always exists and the empty case needs no select
+        // holds 0 -- an upper bound that empties the window like the reference's -1 --, so the upper neighbour always
+        // exists and the empty case needs no select
         uint32_t ms[W1];
 #pragma unroll
         for (int w = 0; w < W1; w++) ms[w] = mq[w] | bit_in_word(v.n1, w);
@@ -513,7 +522,10 @@ struct Chain {
     int ncand = 0;
 #pragma unroll
     for (int w = 0; w < W2; w++) {
-      cand[w] = lds32(v.qmask + (uint32_t)(i * W2 + w) * 4u) & ~md[w] & below(hi - 32 * w) & ~below(lo - 32 * w);
+      // one entry word and word maps: lo and hi are never negative (the map's sentinel elements hold n2 and 0), so the range
+      // masks need no clamping
+      if (W2 == 1 && W1 <= 2) cand[w] = lds32(v.qmask + (uint32_t)i * 4u) & ~md[0] & below_nonneg(hi) & ~below_nonneg(lo);
+      else cand[w] = lds32(v.qmask + (uint32_t)(i * W2 + w) * 4u) & ~md[w] & below(hi - 32 * w) & ~below(lo - 32 * w);
       ncand += __popc(cand[w]);
     }
     int to = -1;
@@ -581,7 +593,7 @@ __device__ __forceinline__ void anneal_entry(const SatsKParams &p, const TeamVie
   }
   if (W1 <= 2) {                                                   // see Chain::move: the window bounds of "nothing mapped below / above"
     Map<true>::put(v.smap, -1, v.mstride, v.n2);
-    Map<true>::put(v.smap, v.n1, v.mstride, -1);
+    Map<true>::put(v.smap, v.n1, v.mstride, 0);        // "nothing mapped above": upper bound 0 = empty window (K:1064-1077 gives -1)
   }
   __syncwarp();
   Chain<W1, W2, LORDER, XORWOW, LSOLN> ch;
