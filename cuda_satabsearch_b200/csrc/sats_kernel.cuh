@@ -11,8 +11,7 @@
 //   * The query blob and every entry blob are brought into shared memory by TMA 1-D bulk copies (cp.async.bulk ...
 //     mbarrier::complete_tx) issued by one thread, each team on its own mbarrier.
 //   * Chain state is bit masks in registers (mapped query SSEs, occupied entry SSEs) plus a map of one 32-bit word per
-//     query SSE (the partner's index pre-multiplied by the 8-byte cell size) in lane-private, bank-conflict-free shared
-//     memory.  The LORDER window and the candidate list of the reference (linear scans, kernel.cu:1053-1083, :677-714)
+//     query SSE (the partner's index) in lane-private, bank-conflict-free shared memory.  The LORDER window and the candidate list of the reference (linear scans, kernel.cu:1053-1083, :677-714)
 //     become O(1) mask arithmetic: bfind/ffs for the neighbouring mapped SSEs, (type mask & ~occupied & range mask) for
 //     the candidates, popc/select-nth for the random pick.  deltasd walks only the *mapped* SSEs (set bits), reading one
 //     8-byte {distance, code} cell per operand; zeta is a 128-byte shared-memory table indexed by the XOR of two codes;
@@ -311,8 +310,9 @@ struct TeamView {
 
 // Lane-private maps (query SSE -> partner entry SSE) in two representations, both laid out so that consecutive lanes own
 // consecutive banks (stride = tw * 4 bytes between a lane's successive words):
-//   Map<true>   one 32-bit word per query SSE holding 8 * partner (-8 = unmapped): one IMAD to address, and the value is
-//               already the byte offset of the partner's cell in a row.  Used for the live map of queries of <= 64 SSEs.
+//   Map<true>   one 32-bit word per query SSE holding the partner (-1 = unmapped): one IMAD to address an element, and one
+//               IMAD turns the loaded partner into the address of its 8-byte cell in a row (holding 8 * partner instead cost
+//               two shifts per move in the window logic).  Used for the live map of queries of <= 64 SSEs.
 //   Map<false>  one byte per query SSE (0xff = unmapped), four to a word.  A quarter of the shared memory, three more
 //               instructions per access: used for the live map of larger queries and for every best-so-far map.
 template <bool WIDE> struct Map {
@@ -321,25 +321,25 @@ template <bool WIDE> struct Map {
     if (WIDE) return base + (uint32_t)k * stride;
     return (uint32_t)(k >> 2) * stride + (base | (uint32_t)(k & 3));      // the lane's slot is 4-byte aligned
   }
-  // 8 * partner of a MAPPED query SSE
+  // 8 * partner of a MAPPED query SSE: the byte offset of the partner's cell within a row of the entry matrix
   static __device__ __forceinline__ uint32_t off8(uint32_t base, int k, uint32_t stride)
   {
     uint32_t v;
     if (WIDE) asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory");
-    else { asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory"); v <<= 3; }
-    return v;
+    else asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory");
+    return v << 3;          // folds into the IMAD that adds the row address
   }
   // partner of a query SSE, -1 if unmapped
   static __device__ __forceinline__ int get(uint32_t base, int k, uint32_t stride)
   {
     int v;
-    if (WIDE) { asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory"); return v >> 3; }
+    if (WIDE) { asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory"); return v; }
     asm("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(addr(base, k, stride)) : "memory");
     return v;
   }
   static __device__ __forceinline__ void put(uint32_t base, int k, uint32_t stride, int j)      // j = -1 unmaps
   {
-    if (WIDE) asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr(base, k, stride)), "r"(j * 8) : "memory");
+    if (WIDE) asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr(base, k, stride)), "r"(j) : "memory");
     else asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr(base, k, stride)), "r"(j) : "memory");
   }
   static __device__ __forceinline__ int words(int n1) { return WIDE ? n1 : (n1 + 3) >> 2; }
@@ -347,7 +347,7 @@ template <bool WIDE> struct Map {
   {
 #pragma unroll 1
     for (int w = 0; w < words(n1); w++)
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (uint32_t)w * stride), "r"(WIDE ? -8 : -1) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (uint32_t)w * stride), "r"(-1) : "memory");
   }
 };
 template <int W1, int W2, bool LORDER, bool XORWOW, bool LSOLN>
