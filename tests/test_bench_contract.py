@@ -27,7 +27,7 @@ def test_reference_arm_prints_one_valid_line():
 
 
 def test_committed_bench_line_has_every_contract_key():
-    d = json.loads((REPO / "profiles" / "r02k_bench.json").read_text())
+    d = json.loads((REPO / "profiles" / "r02z_bench.json").read_text())
     assert REQUIRED | {"gpu_launches", "clocks", "roofline", "cpu_baseline"} <= set(d)
     assert d["higher_is_better"] is True and d["scaling"] in ("weak", "strong") and d["vs_baseline"] is None
     assert d["warmup"] >= 3 and d["gpu_launches"] > 0 and d["data"] == "synthetic"
